@@ -1,0 +1,116 @@
+"""`.weathersandbox` save-file codec.
+
+Restates loadData (reference app.js:1256-1366) and prepareDownload (app.js:6575-6628):
+
+    u32 LE  version id  (263574036; 1939327491 = previous version without settings, app.js:1265)
+    zlib(deflate) of:
+        u16 W, u16 H
+        f32 base [H][W][4]
+        f32 water[H][W][4]
+        i8  wall [H][W][4]
+        f32 droplets[N][5]      N = W*H/25   (app.js:1282, NUM_DROPLETS_DEVIDER = 25)
+        i16 nStations, i16 xy[nStations][2]          (current version only)
+        UTF-8 JSON of guiControls, to end of stream  (current version only)
+
+Rows are bottom-up (GL origin); everything is little endian.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+from dataclasses import dataclass, field
+
+import numpy as np
+
+SAVE_FILE_VERSION_ID = 263574036  # app.js:345
+LEGACY_VERSION_ID = 1939327491  # app.js:1265
+NUM_DROPLETS_DIVIDER = 25  # app.js:452
+
+
+def num_droplets(width: int, height: int) -> int:
+    """app.js:1282 — JS float division; every shipped size divides evenly, otherwise the typed
+    array slicing in loadData effectively floors."""
+    return (width * height) // NUM_DROPLETS_DIVIDER
+
+
+@dataclass
+class SaveFile:
+    width: int
+    height: int
+    base: np.ndarray  # float32 [H][W][4]
+    water: np.ndarray  # float32 [H][W][4]
+    wall: np.ndarray  # int8    [H][W][4]
+    droplets: np.ndarray  # float32 [N][5]
+    stations: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), np.int16))
+    settings_json: str | None = None  # raw guiControls JSON (None for legacy saves)
+    version: int = SAVE_FILE_VERSION_ID
+
+
+class IncompatibleFile(ValueError):
+    """alert('Incompatible file!') at app.js:1349."""
+
+
+def loads(blob: bytes) -> SaveFile:
+    if len(blob) < 4:
+        raise IncompatibleFile("file too short for a version id")
+    (version,) = struct.unpack_from("<I", blob, 0)
+    if version not in (SAVE_FILE_VERSION_ID, LEGACY_VERSION_ID):
+        raise IncompatibleFile(f"unknown save file version id {version}")
+    data = zlib.decompress(blob[4:])
+    w, h = struct.unpack_from("<HH", data, 0)
+    n = w * h
+    nd = num_droplets(w, h)
+    off = 4
+    need = off + n * 16 * 2 + n * 4 + nd * 20
+    if len(data) < need:
+        raise IncompatibleFile(f"payload truncated: {len(data)} < {need} bytes for {w}x{h}")
+    base = np.frombuffer(data, "<f4", n * 4, off).reshape(h, w, 4).copy()
+    off += n * 16
+    water = np.frombuffer(data, "<f4", n * 4, off).reshape(h, w, 4).copy()
+    off += n * 16
+    wall = np.frombuffer(data, "i1", n * 4, off).reshape(h, w, 4).copy()
+    off += n * 4
+    drops = np.frombuffer(data, "<f4", nd * 5, off).reshape(nd, 5).copy()
+    off += nd * 20
+    stations = np.zeros((0, 2), np.int16)
+    settings = None
+    if version == SAVE_FILE_VERSION_ID:
+        (ns,) = struct.unpack_from("<h", data, off)
+        off += 2
+        stations = np.frombuffer(data, "<i2", ns * 2, off).reshape(ns, 2).copy()
+        off += ns * 4
+        settings = data[off:].decode("utf-8")
+    return SaveFile(w, h, base, water, wall, drops, stations, settings, version)
+
+
+def load(path: str) -> SaveFile:
+    with open(path, "rb") as f:
+        return loads(f.read())
+
+
+def payload(sf: SaveFile) -> bytes:
+    """The uncompressed byte stream prepareDownload assembles (app.js:6610-6614)."""
+    h, w = sf.height, sf.width
+    assert sf.base.shape == (h, w, 4) and sf.water.shape == (h, w, 4) and sf.wall.shape == (h, w, 4)
+    parts = [
+        struct.pack("<HH", w, h),
+        np.ascontiguousarray(sf.base, "<f4").tobytes(),
+        np.ascontiguousarray(sf.water, "<f4").tobytes(),
+        np.ascontiguousarray(sf.wall, "i1").tobytes(),
+        np.ascontiguousarray(sf.droplets, "<f4").tobytes(),
+    ]
+    if sf.version == SAVE_FILE_VERSION_ID:
+        st = np.ascontiguousarray(sf.stations, "<i2").reshape(-1, 2)
+        parts.append(struct.pack("<H", st.shape[0]))  # Uint16Array.of(weatherStations.length)
+        parts.append(st.tobytes())
+        parts.append((sf.settings_json or "{}").encode("utf-8"))
+    return b"".join(parts)
+
+
+def dumps(sf: SaveFile, level: int = 6) -> bytes:
+    return struct.pack("<I", sf.version) + zlib.compress(payload(sf), level)
+
+
+def save(path: str, sf: SaveFile, level: int = 6) -> None:
+    with open(path, "wb") as f:
+        f.write(dumps(sf, level))

@@ -1,0 +1,149 @@
+"""Seeded synthetic simulation states for the benchmark / parity configurations.
+
+The generators follow the reference's own new-simulation state (shaders/fragment/setupShader.frag
+:36-92): air cells start at the initial temperature profile with a dew-point spread of 2 K below
+20 % height and 20 K above, wall cells are LAND (soil moisture 25 mm, vegetation, snow above
+2000 m) or WATER (25 C), DISTANCE = 255 -> 127 and VERT_DISTANCE = 100 in air so that the boundary
+pass rebuilds the distance fields.  Terrain here is a deterministic sum of sines instead of the
+shader's sin-hash noise (whose value depends on the GPU's `sin`).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import params as P
+from .savefile import num_droplets
+
+
+def _max_water(t):
+    x = (t / np.float32(250.0)).astype(np.float32)
+    x2 = x * x
+    x4 = x2 * x2
+    x8 = x4 * x4
+    return (x8 * x8 * x).astype(np.float32)
+
+
+def _velocity_field(w, h, seed, amplitude):
+    rng = np.random.default_rng(seed)
+    xs = (np.arange(w, dtype=np.float32) + 0.5) / w
+    ys = (np.arange(h, dtype=np.float32) + 0.5) / h
+    vx = np.zeros((h, w), np.float32)
+    vy = np.zeros((h, w), np.float32)
+    for _ in range(8):  # sum of 8 periodic sines
+        kx, ky = int(rng.integers(1, 6)), int(rng.integers(1, 4))
+        phx, phy = rng.uniform(0, 2 * np.pi, 2)
+        a = np.float32(amplitude / 8.0 * rng.uniform(0.5, 1.5))
+        sx = np.sin(2 * np.pi * kx * xs + phx).astype(np.float32)
+        sy = np.sin(2 * np.pi * ky * ys + phy).astype(np.float32)
+        cx = np.cos(2 * np.pi * kx * xs + phx).astype(np.float32)
+        cy = np.cos(2 * np.pi * ky * ys + phy).astype(np.float32)
+        vx += a * np.outer(cy, sx)
+        vy += a * np.outer(sy, cx)
+    return vx, vy
+
+
+def dry_state(w: int, h: int, seed: int = 1234, g: dict | None = None):
+    """BASELINE config 2: row 0 LAND wall, rest air; T = initial_T[y] + warm blobs; smooth random
+    velocity (amplitude 0.1); P = 0; water = 0.  Returns (base, water, wall)."""
+    g = g or P.resolve_settings(None)
+    t0 = P.initial_T_profile(h, g)
+    rng = np.random.default_rng(seed + 1)
+    base = np.zeros((h, w, 4), np.float32)
+    vx, vy = _velocity_field(w, h, seed, 0.1)
+    base[..., 0] = vx
+    base[..., 1] = vy
+    base[..., 3] = t0[:h, None]
+    xs = np.arange(w, dtype=np.float32)[None, :]
+    ys = np.arange(h, dtype=np.float32)[:, None]
+    for _ in range(16):  # warm / cold blobs, 0.5 K
+        cx, cy = rng.uniform(0, w), rng.uniform(0.1 * h, 0.9 * h)
+        r = rng.uniform(0.02, 0.08) * h
+        dx = np.minimum(np.abs(xs - cx), w - np.abs(xs - cx))
+        amp = np.float32(rng.normal(0.0, 0.5))
+        base[..., 3] += amp * np.exp(-((dx * dx + (ys - cy) ** 2) / np.float32(r * r))).astype(np.float32)
+    water = np.zeros((h, w, 4), np.float32)
+    wall = np.zeros((h, w, 4), np.int8)
+    wall[..., 0] = 1
+    wall[..., 1] = np.minimum(np.arange(h), 127)[:, None]
+    wall[..., 2] = np.minimum(np.arange(h), 127)[:, None]
+    base[0, :, 0:2] = 0.0
+    base[0, :, 3] = 1000.0
+    water[0, :, 0] = 1001.0
+    return base, water, wall
+
+
+def terrain_height(w: int, h: int, seed: int = 7) -> np.ndarray:
+    """Surface row index per column: sea (row 0 only) on ~30 % of the columns, hills up to ~12 % of
+    the height elsewhere."""
+    rng = np.random.default_rng(seed)
+    x = (np.arange(w) + 0.5) / w
+    hgt = np.zeros(w)
+    for k in (1, 2, 3, 5, 8, 13):
+        hgt += np.sin(2 * np.pi * k * x + rng.uniform(0, 2 * np.pi)) / k
+    hgt = (hgt - hgt.min()) / (hgt.max() - hgt.min())  # 0..1
+    sea = hgt < 0.3
+    rows = np.where(sea, 0, 1 + np.floor((hgt - 0.3) / 0.7 * 0.12 * h)).astype(np.int64)
+    return rows
+
+
+def full_state(w: int, h: int, seed: int = 7, g: dict | None = None, with_droplets: bool = True,
+               n_droplets: int | None = None, vel_amplitude: float = 0.05):
+    """BASELINE configs 3-5: terrain + sea, setupShader-style thermodynamic profile, a weak smooth
+    wind field so that advection has work to do.  Returns (base, water, wall, droplets)."""
+    g = g or P.resolve_settings(None)
+    t0 = P.initial_T_profile(h, g)
+    lapse = np.float32(P.dry_lapse(g))
+    rows = terrain_height(w, h, seed)
+    yy = np.arange(h)[:, None]
+    is_wall = yy <= rows[None, :]
+    sea = (rows == 0)[None, :]
+
+    base = np.zeros((h, w, 4), np.float32)
+    water = np.zeros((h, w, 4), np.float32)
+    wall = np.zeros((h, w, 4), np.int8)
+
+    texy = ((np.arange(h, dtype=np.float32) + np.float32(0.5)) * np.float32(1.0 / h))[:, None]
+    pot = t0[:h, None].astype(np.float32)
+    real = (pot - texy * lapse).astype(np.float32)
+    spread = np.where(texy < 0.20, np.float32(2.0), np.float32(20.0)).astype(np.float32)
+    total = _max_water(real - spread)
+    cloud = np.maximum(total - _max_water(real), np.float32(0.0))
+    vx, vy = _velocity_field(w, h, seed + 11, vel_amplitude)
+
+    air = ~is_wall
+    base[..., 0] = np.where(air, vx, 0)
+    base[..., 1] = np.where(air, vy, 0)
+    base[..., 3] = np.where(air, np.broadcast_to(pot, (h, w)), 0)
+    water[..., 0] = np.where(air, np.broadcast_to(total, (h, w)), 0)
+    water[..., 1] = np.where(air, np.broadcast_to(cloud, (h, w)), 0)
+
+    # wall cells (setupShader.frag:65-78)
+    land = is_wall & ~sea
+    seaw = is_wall & sea
+    base[..., 3] = np.where(seaw, np.float32(P.c_to_k(25.0)), base[..., 3])
+    water[..., 2] = np.where(land, np.float32(25.0), water[..., 2])
+    xs = np.arange(w)
+    veg = np.clip(60 + 50 * np.sin(2 * np.pi * 3 * (xs + 0.5) / w) - rows * (300.0 / h), 0, 127).astype(np.int8)
+    height_m = rows * (g["simHeight"] / h)
+    snow = np.clip((height_m - 2000.0) / 3000.0 * 100.0, 0.0, 100.0).astype(np.float32)
+    wall[..., 3] = np.where(land, veg[None, :], 0)
+    water[..., 3] = np.where(land, snow[None, :], water[..., 3])
+    wall[..., 0] = np.where(sea, 2, 1)  # air copies the type below on the first boundary pass anyway
+    wall[..., 1] = np.where(is_wall, 0, 127)
+    vd = np.clip(yy - rows[None, :], -128, 127)
+    wall[..., 2] = np.where(is_wall, vd, 100).astype(np.int8)
+
+    drops = None
+    if with_droplets:
+        nd = n_droplets if n_droplets is not None else num_droplets(w, h)
+        drops = init_rain_drops(nd, seed + 42)
+    return base, water, wall, drops
+
+
+def init_rain_drops(n: int, seed: int = 42) -> np.ndarray:
+    """initRainDrops (app.js:4901-4913) with a seeded generator instead of Math.random():
+    every droplet starts inactive (water mass in [-10,-9)) and the slots hold RNG seeds."""
+    rng = np.random.default_rng(seed)
+    d = rng.random((n, 5), dtype=np.float32)
+    d[:, 2] = np.float32(-10.0) + d[:, 2]
+    return d

@@ -1,0 +1,230 @@
+/*
+ * wsb200.h — C ABI of libwsb200.so, the B200-native simulation core that replaces the
+ * per-iteration simulation loop of 2D-Weather-Sandbox (reference: app.js:5830-6005 and the GLSL
+ * passes it draws).  The reference has no plugin/FFI interface for this path: the boundary is the
+ * set of WebGL interactions between app.js and the simulation state.  Each export below names the
+ * reference interaction (file:line, relative to the reference checkout) it replaces one-for-one.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; every function returns 0 on success, non-zero
+ *     on failure with a message available from wsb_last_error() (the reference path has no error
+ *     channel: GL errors are silent, shader failures throw strings at app.js:6644,6706).
+ *   - the caller owns every host buffer; no pointer is retained after a call returns.
+ *   - field layouts are exactly the reference's packed texture / save-file layouts:
+ *       base  float[H][W][4]  (vx, vy, pressure, potential temperature)   RGBA32F  app.js:5122-5126
+ *       water float[H][W][4]  (total, cloud, precip|soil moisture, smoke|snow)     app.js:5128-5133
+ *       wall  int8 [H][W][4]  (type, distance, vertical distance, vegetation) RGBA8I app.js:5135-5139
+ *       light float[H][W][4]  (sunlight, net heating, IR down, IR up)              app.js:5141-5145
+ *       droplets float[N][5]  (x, y in [-1,1], water mass, ice mass, density)      app.js:4901-4913
+ *     row 0 is the bottom row (GL origin), x is the fastest index.
+ *   - all calls for one sim arrive from one host thread, in order (JS is single threaded).
+ *     wsb_step is asynchronous (it only enqueues work, like the reference's draw calls); the read
+ *     functions synchronise, like gl.readPixels.
+ */
+#ifndef WSB200_H
+#define WSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSB_ABI_VERSION 1
+
+typedef struct wsb_sim wsb_sim;
+
+/* Size of an opaque NCCL bootstrap id (ncclUniqueId is 128 bytes). */
+#define WSB_COMM_ID_BYTES 128
+
+/* Replaces the allocation of the simulation textures / FBOs / droplet buffers
+ * (app.js:5149-5317, 4885-5002).  For a multi-GPU run the grid is cut into x-strips, one process
+ * per GPU: rank r owns global columns [x_begin, x_begin + local_width). */
+typedef struct wsb_config {
+  int32_t abi_version;   /* must be WSB_ABI_VERSION */
+  int32_t width;         /* global sim_res_x */
+  int32_t height;        /* sim_res_y */
+  int32_t n_droplets;    /* NUM_DROPLETS (app.js:1282: W*H/25); 0 = no particle system */
+  int32_t device;        /* CUDA device ordinal for this process */
+  int32_t rank;          /* 0 .. n_ranks-1 */
+  int32_t n_ranks;       /* 1 = single GPU */
+  int32_t schedule;      /* WSB_SCHEDULE_* */
+  uint8_t comm_id[WSB_COMM_ID_BYTES]; /* from wsb_comm_id_create on rank 0 (n_ranks > 1) */
+} wsb_config;
+
+enum {
+  WSB_SCHEDULE_FUSED = 0,     /* product path: fused sm_100a kernels */
+  WSB_SCHEDULE_REFERENCE = 1  /* one kernel per reference pass, same order as app.js:5830-6005
+                                 (used for per-pass parity checks and as a perf baseline) */
+};
+
+/* Scalar uniforms of the simulation programs: static (app.js:5478-5640) and GUI-driven
+ * (setGuiUniforms, app.js:3401-3443).  Names are the GLSL uniform names. */
+typedef struct wsb_params {
+  float dragMultiplier;          /* velocityShader.frag:16 */
+  float wind;                    /* velocityShader.frag:18 */
+  float vorticity;               /* boundaryShader.frag:26 */
+  float landEvaporation;         /* boundaryShader.frag:28 */
+  float waterEvaporation;        /* boundaryShader.frag:27 */
+  float dynamicWaterTemperature; /* boundaryShader.frag:38 (0.0 or 1.0) */
+  float evapHeat;                /* boundary/advection/precipitation */
+  float waterWeight;             /* boundaryShader.frag:29 */
+  float meltingHeat;             /* advectionShader.frag:35, precipitationShader.vert:38 */
+  float condensationRate;        /* advectionShader.frag:36 */
+  float globalDrying;            /* advectionShader.frag:40 */
+  float globalHeating;           /* advectionShader.frag:41 */
+  float soundingForcing;         /* advectionShader.frag:42 */
+  float globalEffectsStartAlt;   /* already divided by simHeight (app.js:3425) */
+  float globalEffectsEndAlt;     /* already divided by simHeight (app.js:3426) */
+  float waterTemperature;        /* Kelvin (app.js:3427) */
+  float greenhouseGases;         /* lightingShader.frag:27 */
+  float waterGreenHouseEffect;   /* lightingShader.frag:28 */
+  float IR_rate;                 /* lightingShader.frag:25 */
+  float dryLapse;                /* app.js:5439 */
+  float aboveZeroThreshold;      /* precipitationShader.vert:41-50 */
+  float subZeroThreshold;
+  float spawnChanceMult;         /* guiControls.spawnChance (app.js:3433) */
+  float snowDensity;
+  float fallSpeed;
+  float growthRate0C;
+  float growthRate_30C;
+  float freezingRate;
+  float meltingRate;
+  float evapRate;
+  int32_t enablePrecipitation;   /* guiControls.enablePrecipitation (app.js:5936) */
+  int32_t reserved;
+} wsb_params;
+
+/* Per-frame uniforms: sun (updateSunlight, app.js:6557-6561), brush (app.js:5750-5808) and
+ * airplane (app.js:3335).  They stay constant for all iterations of one wsb_step call, exactly
+ * like the reference which sets them once per draw(). */
+typedef struct wsb_frame_inputs {
+  float sunAngle;           /* solar zenith angle in radians (app.js:6538-6539) */
+  float sunIntensity;       /* W/m2 (app.js:6550) */
+  float userInputValues[4]; /* x, y (normalised), intensity, brush size (advectionShader.frag:21) */
+  float userInputMove[2];   /* advectionShader.frag:26 */
+  int32_t userInputType;    /* advectionShader.frag:27; -1 = none */
+  int32_t wrapHorizontally; /* advectionShader.frag:31 */
+  float airplaneValues[4];  /* advectionShader.frag:29 */
+} wsb_frame_inputs;
+
+/* Fields readable through wsb_read_rect — the textures app.js reads with gl.readPixels. */
+enum {
+  WSB_FIELD_BASE = 0,       /* float4 */
+  WSB_FIELD_WATER = 1,      /* float4 */
+  WSB_FIELD_WALL = 2,       /* int8 x4 */
+  WSB_FIELD_LIGHT = 3,      /* float4 */
+  WSB_FIELD_FEEDBACK = 4,   /* float4 precipitationFeedbackTexture */
+  WSB_FIELD_DEPOSITION = 5, /* float2 precipitationDepositionTexture */
+  WSB_FIELD_CURL = 6,       /* float  (REFERENCE schedule only; the fused path never stores it) */
+  WSB_FIELD_VORTFORCE = 7   /* float2 (REFERENCE schedule only) */
+};
+
+/* Which copy of a ping-pong pair a read returns. */
+enum {
+  WSB_VIEW_FRAMEBUFF_0 = 0, /* what the reference reads and saves: frameBuff_0 = base after the
+                               pressure pass, water after the boundary pass, wall_0; light =
+                               lightTexture_0 (app.js:6586-6593, 1082-1176) */
+  WSB_VIEW_FRAMEBUFF_1 = 1, /* frameBuff_1 = base/water/wall after the advection pass; light =
+                               lightTexture_1 */
+  WSB_VIEW_LATEST = 2       /* light: the texture written by the last lighting pass; others as _0 */
+};
+
+/* --- lifecycle ------------------------------------------------------------------------------ */
+
+/* Rank 0 of a multi-GPU job creates the bootstrap id and hands it to the other processes by any
+ * host-side channel (the Python host uses torch.distributed broadcast). */
+int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]);
+
+/* app.js:5149-5317 + 4885-5002: allocate state; light, feedback, deposition, lightning, curl and
+ * vortForce start zero-filled (texImage2D(..., null)); iterNum = 0, even = true. */
+int wsb_create(const wsb_config* cfg, wsb_sim** out);
+
+/* page unload */
+int wsb_destroy(wsb_sim* sim);
+
+/* app.js:5189-5234 (both ping-pong copies receive the same arrays) and 4917-4962 (both droplet
+ * buffers).  Arrays are GLOBAL-size ([H][W][4] ...); every rank passes the same arrays and keeps
+ * its own strip.  Also resets iterNum, even, light/feedback/lightning like a page load.
+ * drops may be NULL when n_droplets == 0. Also used for the 'L' reload key (app.js:4628-4640). */
+int wsb_upload(wsb_sim* sim, const float* base, const float* water, const int8_t* wall,
+               const float* drops);
+
+/* setGuiUniforms + the static uniforms (app.js:3401-3443, 5478-5640). */
+int wsb_set_params(wsb_sim* sim, const wsb_params* p);
+
+/* uniform arrays initial_Tv / realWorldSounding_{T,W,Vel}v (app.js:5444-5474, 5485-5502), here
+ * generalised to length height+1 (the reference caps them at 504 entries).  Sounding arrays may
+ * be NULL (= all zero, 'No valid sounding loaded', app.js:5462). */
+int wsb_set_profiles(wsb_sim* sim, const float* initial_T, const float* sounding_T,
+                     const float* sounding_W, const float* sounding_Vel);
+
+/* updateSunlight / brush / airplane uniforms, once per frame. */
+int wsb_set_frame_inputs(wsb_sim* sim, const wsb_frame_inputs* in);
+
+/* --- the hot path --------------------------------------------------------------------------- */
+
+/* The body of `for (i < IterPerFrame)` in draw() (app.js:5830-6005), n_iters times: velocity,
+ * curl, vorticity, boundary, advection, pressure, lighting, feedback clear, precipitation
+ * particles, inactive-droplet latch every 600 iterations (on device, no host sync), lightning
+ * latch, iterNum++.  Asynchronous. */
+int wsb_step(wsb_sim* sim, int32_t n_iters);
+
+/* Block until everything enqueued so far has finished (gl.finish). */
+int wsb_sync(wsb_sim* sim);
+
+/* Run ONE reference pass (WSB_PASS_*) on the current buffers — REFERENCE schedule only; used by
+ * the per-pass parity tests. */
+enum {
+  WSB_PASS_VELOCITY = 0, WSB_PASS_CURL = 1, WSB_PASS_VORTICITY = 2, WSB_PASS_BOUNDARY = 3,
+  WSB_PASS_ADVECTION = 4, WSB_PASS_PRESSURE = 5, WSB_PASS_LIGHTING = 6, WSB_PASS_PRECIPITATION = 7
+};
+int wsb_debug_run_pass(wsb_sim* sim, int32_t pass);
+
+/* The "dry sweep" of BASELINE config 2: velocity -> advection of the base field -> pressure, fused
+ * into one kernel, n_iters times.  Water, light and droplets are not touched. */
+int wsb_step_dry(wsb_sim* sim, int32_t n_iters);
+
+/* --- readbacks (gl.readPixels / getBufferSubData call sites) --------------------- */
+
+/* Rectangle [x, x+w) x [y, y+h) in GLOBAL cell coordinates, no wrap (callers wrap themselves,
+ * app.js:3061-3066).  A rank only fills the part of the rectangle inside its own strip and
+ * leaves the rest of dst untouched; dst is a dense [h][w][channels] array. Synchronises. */
+int wsb_read_rect(wsb_sim* sim, int32_t field, int32_t view, int32_t x, int32_t y, int32_t w,
+                  int32_t h, void* dst);
+
+/* app.js:5017-5019, 5084-5086, 6595-6597. buffer: 0/1 = precipVertexBuffer_0/_1, 2 = the one
+ * written last. */
+int wsb_read_droplets(wsb_sim* sim, int32_t buffer, int32_t first, int32_t count, float* dst);
+
+/* app.js:5957-5967: the value latched into the `inactiveDroplets` uniform. */
+int wsb_get_inactive_droplets(wsb_sim* sim, float* out);
+
+/* app.js:5985-5994: the 1x1 lightningDataTexture. */
+int wsb_get_lightning(wsb_sim* sim, float out[4]);
+
+/* iterNum (app.js:440). */
+int wsb_get_iter(wsb_sim* sim, int64_t* out);
+
+/* Local strip of this rank: [x_begin, x_begin + local_width). */
+int wsb_get_strip(wsb_sim* sim, int32_t* x_begin, int32_t* local_width);
+
+/* Largest |v| component seen by the advection kernel since upload (cells / iteration); the fused
+ * kernels stay exact for any value, multi-GPU strips require it below the ghost-zone budget. */
+int wsb_get_max_velocity(wsb_sim* sim, float* out);
+
+/* Number of kernels launched by this sim since creation (bench evidence). */
+int wsb_get_launch_count(wsb_sim* sim, int64_t* out);
+
+/* Milliseconds of device time between two internal CUDA events bracketing the most recent
+ * wsb_step / wsb_step_dry call on the sim's stream (bench: the stream is library-owned, so
+ * torch.cuda.Event cannot see it). Synchronises. */
+int wsb_last_step_ms(wsb_sim* sim, float* out);
+
+const char* wsb_last_error(void);
+const char* wsb_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSB200_H */
