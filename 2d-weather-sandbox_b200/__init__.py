@@ -11,7 +11,7 @@ does in JavaScript, the x-strip plan and a ctypes binding of the C ABI (include/
 simulation arithmetic runs in csrc/libwsb200.so (hand-written sm_100a CUDA); there is no CPU
 fallback — constructing a `Simulation` without the built library raises.
 """
-from . import params, savefile, strips, synth  # noqa: F401
+from . import multi, params, savefile, strips, synth  # noqa: F401
 from .sim import Simulation, load_library, library_path  # noqa: F401
 
-__all__ = ["params", "savefile", "strips", "synth", "Simulation", "load_library", "library_path"]
+__all__ = ["multi", "params", "savefile", "strips", "synth", "Simulation", "load_library", "library_path"]

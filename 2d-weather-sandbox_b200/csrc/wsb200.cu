@@ -1,0 +1,896 @@
+// wsb200.cu — host side of libwsb200.so: the C ABI of include/wsb200.h over the sm_100a kernels.
+//
+// One wsb_sim = one process / one GPU.  State lives in HBM in exactly the reference's packed
+// texture layouts (base / water / light RGBA32F, wall RGBA8I, feedback RGBA32F, deposition RG32F,
+// droplets 5 x f32), row 0 = bottom row, x fastest.  A multi-GPU run cuts the grid into x-strips,
+// one per rank, each stored with kGhost ghost columns on both sides; the ring of ranks refreshes
+// the ghost columns once per iteration with ncclSend/ncclRecv over NVLink (x is periodic, so rank
+// 0 and rank N-1 are neighbours).
+//
+// Schedules
+//   WSB_SCHEDULE_REFERENCE  one kernel per reference pass, in the order of app.js:5830-6005.
+//                           Canonical state after an iteration: base_0 / water_0 / wall_0.
+//   WSB_SCHEDULE_FUSED      k_fused_pvb + k_fused_adv (+ k_precipitation, k_latch) per iteration.
+//                           Canonical state: base_1 / water_1 / wall_1 (the advection output) with
+//                           the iteration's pressure pass still pending; it runs as the first
+//                           stage of the next k_fused_pvb, or on demand inside wsb_read_rect.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/wsb200.h"
+#include "wsb_fused_kernels.cuh"
+#include "wsb_particles.cuh"
+#include "wsb_ref_kernels.cuh"
+
+using namespace wsb;
+
+namespace {
+
+constexpr int kGhost = 8;  // == strips.GHOST on the Python side
+
+thread_local char g_err[512] = "";
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (a single-GPU process never needs it; a multi-GPU host process has
+// normally loaded torch's bundled libnccl.so.2 already and dlopen returns that same image).
+// ---------------------------------------------------------------------------------------------
+struct Id128 { char internal[WSB_COMM_ID_BYTES]; };
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclChar = 0;  // ncclInt8 / ncclChar
+
+int load_nccl() {
+  if (g_nccl.handle) return 0;
+  const char* names[] = {getenv("WSB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    if (!n || !*n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail("cannot load libnccl.so.2 (%s); set WSB_NCCL_LIB", dlerror());
+#define SYM(field, name)                                                  \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                              \
+  if (!g_nccl.field) return fail("libnccl: missing symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.handle = h;
+  return 0;
+}
+#define NCK(call)                                                                          \
+  do {                                                                                     \
+    int r_ = (call);                                                                       \
+    if (r_ != 0) return fail("%s failed: %s", #call, g_nccl.GetErrorString(r_));           \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// halo pack / unpack: ghost columns are strided in the x-fastest layout; they travel as
+// contiguous [side][row][kGhost] blocks.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_halo(const T* __restrict__ f, int pitch, int H, int lw, T* __restrict__ toLeft,
+                            T* __restrict__ toRight) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * kGhost) return;
+  const int y = t / kGhost, i = t - y * kGhost;
+  toLeft[t] = f[(size_t)y * pitch + kGhost + i];   // my leftmost owned columns
+  toRight[t] = f[(size_t)y * pitch + lw + i];      // my rightmost owned columns
+}
+template <typename T>
+__global__ void k_unpack_halo(T* __restrict__ f, int pitch, int H, int lw, const T* __restrict__ fromLeft,
+                              const T* __restrict__ fromRight) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= H * kGhost) return;
+  const int y = t / kGhost, i = t - y * kGhost;
+  f[(size_t)y * pitch + i] = fromLeft[t];
+  f[(size_t)y * pitch + kGhost + lw + i] = fromRight[t];
+}
+
+}  // namespace
+
+struct wsb_sim {
+  wsb_config cfg;
+  int W, H, ND;
+  int x_begin, lw, ghost, pitch;
+  int schedule;
+  Geom g;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+
+  float4 *base[2] = {}, *water[2] = {}, *light[2] = {}, *fb = nullptr;
+  char4* wall[2] = {};
+  float2 *dep = nullptr, *vort = nullptr;
+  float* curl = nullptr;
+  float* drops[2] = {};
+  float *initial_T = nullptr, *sndT = nullptr, *sndW = nullptr, *sndV = nullptr;
+  float* lightning = nullptr;  // 4 floats: lightningDataTexture
+  float* inactive = nullptr;   // the `inactiveDroplets` uniform, kept on the device
+  unsigned* maxv = nullptr;
+  float4* scratch = nullptr;   // read_rect staging
+  size_t scratch_cells = 0;
+
+  DevParams dp;
+  long long iter = 0;
+  bool even = true;
+  int last_drops = 0;
+  bool pressure_pending = false;  // FUSED: base_1 still needs the pressure pass
+  bool fb_dirty = false;          // feedback / deposition hold non-zero data
+  long long launches = 0;
+
+  // per-kernel-class device timing (wsb_set_profiling): events around every launch of a step call
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int kind; size_t e0, e1; };
+  std::vector<Span> spans;
+
+  // multi-GPU
+  void* comm = nullptr;
+  unsigned char *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
+  size_t halo_bytes = 0;
+};
+
+namespace {
+
+size_t cells(const wsb_sim* s) { return (size_t)s->pitch * s->H; }
+
+GlobalCtx make_ctx(const wsb_sim* s, int b, int w, int wl, int l) {
+  GlobalCtx c;
+  c.base = s->base[b];
+  c.water = s->water[w];
+  c.wall = s->wall[wl];
+  c.vortf = s->vort;
+  c.light = s->light[l];
+  c.fb = s->fb;
+  c.dep = s->dep;
+  c.g = s->g;
+  return c;
+}
+
+void refresh_derived(wsb_sim* s) {
+  s->dp.sinSun = (float)sin((double)s->dp.in.sunAngle);
+  s->dp.cosSun = (float)cos((double)s->dp.in.sunAngle);
+}
+void set_iter_uniform(wsb_sim* s) {
+  s->dp.iterNum = (float)s->iter;
+  s->dp.iterI = (int)s->dp.iterNum;
+}
+
+dim3 grid2d(const wsb_sim* s, int bx, int by) { return dim3((s->pitch + bx - 1) / bx, (s->H + by - 1) / by); }
+
+int check_launch(wsb_sim* s, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+  s->launches++;
+  return 0;
+}
+#define LAUNCHED(what) \
+  do { if (check_launch(s, what)) return 1; } while (0)
+
+// --- per-kernel timing -----------------------------------------------------------------------
+size_t prof_mark(wsb_sim* s) {
+  if (s->ev_used == s->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    s->ev_pool.push_back(e);
+  }
+  cudaEventRecord(s->ev_pool[s->ev_used], s->stream);
+  return s->ev_used++;
+}
+struct ProfScope {  // brackets the launches of one kernel class
+  wsb_sim* s; int kind; size_t e0;
+  ProfScope(wsb_sim* s_, int k) : s(s_), kind(k), e0(0) { if (s->profiling) e0 = prof_mark(s); }
+  ~ProfScope() { if (s->profiling) s->spans.push_back({kind, e0, prof_mark(s)}); }
+};
+
+// --- halo exchange ---------------------------------------------------------------------------
+struct HaloField { void* ptr; int elt; };
+
+int exchange(wsb_sim* s, const std::vector<HaloField>& fields) {
+  if (s->cfg.n_ranks <= 1) return 0;
+  ProfScope prof(s, WSB_KERNEL_HALO);
+  const int n = s->H * kGhost;
+  const int threads = 256, blocks = (n + threads - 1) / threads;
+  size_t off = 0;
+  for (const HaloField& f : fields) {
+    if (f.elt == 16)
+      k_pack_halo<float4><<<blocks, threads, 0, s->stream>>>((const float4*)f.ptr, s->pitch, s->H, s->lw,
+                                                             (float4*)(s->sendL + off), (float4*)(s->sendR + off));
+    else
+      k_pack_halo<int><<<blocks, threads, 0, s->stream>>>((const int*)f.ptr, s->pitch, s->H, s->lw,
+                                                          (int*)(s->sendL + off), (int*)(s->sendR + off));
+    LAUNCHED("k_pack_halo");
+    off += (size_t)n * f.elt;
+  }
+  if (off > s->halo_bytes) return fail("halo staging overflow");
+  const int left = (s->cfg.rank + s->cfg.n_ranks - 1) % s->cfg.n_ranks;
+  const int right = (s->cfg.rank + 1) % s->cfg.n_ranks;
+  // Sends go (left, right); receives are posted (right, left) so that with two ranks — where both
+  // neighbours are the same peer and NCCL matches operations in call order — the block a rank
+  // sends to its left neighbour lands in that neighbour's RIGHT ghost zone.
+  NCK(g_nccl.GroupStart());
+  NCK(g_nccl.Send(s->sendL, off, kNcclChar, left, s->comm, s->stream));
+  NCK(g_nccl.Send(s->sendR, off, kNcclChar, right, s->comm, s->stream));
+  NCK(g_nccl.Recv(s->recvR, off, kNcclChar, right, s->comm, s->stream));
+  NCK(g_nccl.Recv(s->recvL, off, kNcclChar, left, s->comm, s->stream));
+  NCK(g_nccl.GroupEnd());
+  s->launches++;
+  off = 0;
+  for (const HaloField& f : fields) {
+    if (f.elt == 16)
+      k_unpack_halo<float4><<<blocks, threads, 0, s->stream>>>((float4*)f.ptr, s->pitch, s->H, s->lw,
+                                                               (const float4*)(s->recvL + off), (const float4*)(s->recvR + off));
+    else
+      k_unpack_halo<int><<<blocks, threads, 0, s->stream>>>((int*)f.ptr, s->pitch, s->H, s->lw,
+                                                            (const int*)(s->recvL + off), (const int*)(s->recvR + off));
+    LAUNCHED("k_unpack_halo");
+    off += (size_t)n * f.elt;
+  }
+  return 0;
+}
+
+// --- reference schedule ----------------------------------------------------------------------
+const dim3 kRefBlock(64, 4);
+
+int ref_velocity(wsb_sim* s) {
+  k_ref_velocity<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 0, 0, 0, 0), s->dp, s->base[1], s->wall[1]);
+  LAUNCHED("k_ref_velocity");
+  return 0;
+}
+int ref_curl(wsb_sim* s) {
+  k_ref_curl<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->curl);
+  LAUNCHED("k_ref_curl");
+  return 0;
+}
+int ref_vorticity(wsb_sim* s) {
+  k_ref_vorticity<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(s->g, s->curl, s->vort);
+  LAUNCHED("k_ref_vorticity");
+  return 0;
+}
+int ref_boundary(wsb_sim* s) {
+  set_iter_uniform(s);
+  k_ref_boundary<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->initial_T, s->base[0],
+                                                                s->water[0], s->wall[0]);
+  LAUNCHED("k_ref_boundary");
+  return 0;
+}
+int ref_advection(wsb_sim* s, bool dry) {
+  GlobalCtx c = make_ctx(s, 0, 0, 0, 0);
+  if (dry)
+    k_ref_advection<true><<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(c, s->dp, s->initial_T, s->sndT, s->sndW, s->sndV,
+                                                                         s->base[1], s->water[1], s->wall[1], s->maxv);
+  else
+    k_ref_advection<false><<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(c, s->dp, s->initial_T, s->sndT, s->sndW, s->sndV,
+                                                                          s->base[1], s->water[1], s->wall[1], s->maxv);
+  LAUNCHED("k_ref_advection");
+  return 0;
+}
+int ref_pressure(wsb_sim* s) {
+  k_ref_pressure<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->base[0], s->wall[0]);
+  LAUNCHED("k_ref_pressure");
+  return 0;
+}
+int ref_lighting(wsb_sim* s) {
+  const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;  // app.js:5912-5926
+  k_ref_lighting<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, src), s->dp, s->light[dst]);
+  LAUNCHED("k_ref_lighting");
+  s->even = !s->even;
+  return 0;
+}
+
+// feedback clear (app.js:5933-5934) as a separate step: REFERENCE schedule, and FUSED when the
+// clear cannot ride on k_fused_pvb.
+int clear_feedback(wsb_sim* s) {
+  if (!s->fb_dirty) return 0;
+  CK(cudaMemsetAsync(s->fb, 0, cells(s) * sizeof(float4), s->stream));
+  CK(cudaMemsetAsync(s->dep, 0, cells(s) * sizeof(float2), s->stream));
+  s->launches += 2;
+  s->fb_dirty = false;
+  return 0;
+}
+
+// precipitation particles + latches (app.js:5936-5983).  `even` has already been toggled by the
+// lighting step: the source buffer is the one selected BEFORE the toggle.
+int precipitation(wsb_sim* s) {
+  if (!s->dp.p.enablePrecipitation || s->ND == 0) return 0;
+  if (s->cfg.n_ranks > 1) return fail("precipitation particles are single-GPU only (SURVEY 8e)");
+  const int src = s->even ? 1 : 0, dst = s->even ? 0 : 1;
+  set_iter_uniform(s);
+  ProfScope prof(s, WSB_KERNEL_PRECIP);
+  const int threads = 256, blocks = (s->ND + threads - 1) / threads;
+  k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1], s->water[1], s->fb, s->dep,
+                                                     s->lightning, s->inactive, s->g, s->dp, s->ND);
+  LAUNCHED("k_precipitation");
+  s->fb_dirty = true;
+  s->last_drops = dst;
+  k_latch<<<1, 32, 0, s->stream>>>(s->fb, s->inactive, s->lightning, s->dp.iterNum, (s->iter % 600 == 0) ? 1 : 0);
+  LAUNCHED("k_latch");
+  return 0;
+}
+
+int ref_iteration(wsb_sim* s) {
+  if (ref_velocity(s) || ref_curl(s) || ref_vorticity(s) || ref_boundary(s) || ref_advection(s, false) ||
+      ref_pressure(s) || ref_lighting(s) || clear_feedback(s) || precipitation(s))
+    return 1;
+  s->iter++;
+  return 0;
+}
+
+// --- fused schedule --------------------------------------------------------------------------
+dim3 tile_grid(const wsb_sim* s) { return dim3((s->pitch + kTX - 1) / kTX, (s->H + kTY - 1) / kTY); }
+
+int fused_iteration(wsb_sim* s) {
+  set_iter_uniform(s);
+  const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;
+  const bool particles = s->dp.p.enablePrecipitation && s->ND > 0;
+  // pressure(previous iteration) -> velocity -> curl -> vorticity -> boundary; also clears the
+  // feedback / deposition cells it has consumed (app.js:5933-5934 folded in)
+  {
+    ProfScope prof(s, WSB_KERNEL_PVB);
+    k_fused_pvb<<<tile_grid(s), kNT, kSmem1, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->initial_T,
+                                                           s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
+                                                           s->base[0], s->water[0], s->wall[0]);
+    LAUNCHED("k_fused_pvb");
+  }
+  s->fb_dirty = false;
+  // advection (+ condensation ...) -> lighting
+  {
+    ProfScope prof(s, WSB_KERNEL_ADV);
+    k_fused_adv<<<tile_grid(s), kNT, kSmem2, s->stream>>>(make_ctx(s, 0, 0, 0, src), s->dp, s->initial_T, s->sndT, s->sndW,
+                                                           s->sndV, s->base[1], s->water[1], s->wall[1], s->light[dst], s->maxv);
+    LAUNCHED("k_fused_adv");
+  }
+  s->even = !s->even;
+  s->pressure_pending = true;
+  if (particles && precipitation(s)) return 1;
+  if (exchange(s, {{s->base[1], 16}, {s->water[1], 16}, {s->wall[1], 4}, {s->light[dst], 16}})) return 1;
+  s->iter++;
+  return 0;
+}
+
+int dry_iteration(wsb_sim* s) {
+  if (s->schedule == WSB_SCHEDULE_REFERENCE) {
+    // velocity renders into frameBuff_1, advection samples frameBuff_0 (app.js:5832-5890): with the
+    // boundary pass left out, velocity's output is handed over unchanged.
+    if (ref_velocity(s)) return 1;
+    std::swap(s->base[0], s->base[1]);
+    std::swap(s->wall[0], s->wall[1]);
+    if (ref_advection(s, true) || ref_pressure(s)) return 1;
+  } else {
+    // canonical FUSED state is base_1 with no pressure pending after a dry sweep
+    if (s->pressure_pending) return fail("wsb_step_dry after wsb_step is not supported on the FUSED schedule");
+    {
+      ProfScope prof(s, WSB_KERNEL_DRY);
+      k_fused_dry<<<tile_grid(s), kNT, kSmem3, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->base[0], s->maxv);
+      LAUNCHED("k_fused_dry");
+    }
+    std::swap(s->base[0], s->base[1]);
+    if (exchange(s, {{s->base[1], 16}})) return 1;
+  }
+  s->iter++;
+  return 0;
+}
+
+int alloc_all(wsb_sim* s) {
+  const size_t n = cells(s);
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&s->base[k], n * sizeof(float4)));
+    CK(cudaMalloc(&s->water[k], n * sizeof(float4)));
+    CK(cudaMalloc(&s->wall[k], n * sizeof(char4)));
+    CK(cudaMalloc(&s->light[k], n * sizeof(float4)));
+    if (s->ND) CK(cudaMalloc(&s->drops[k], (size_t)s->ND * 5 * sizeof(float)));
+  }
+  CK(cudaMalloc(&s->fb, n * sizeof(float4)));
+  CK(cudaMalloc(&s->dep, n * sizeof(float2)));
+  if (s->schedule == WSB_SCHEDULE_REFERENCE) {
+    CK(cudaMalloc(&s->curl, n * sizeof(float)));
+    CK(cudaMalloc(&s->vort, n * sizeof(float2)));
+  }
+  const size_t np = (size_t)s->H + 2;
+  CK(cudaMalloc(&s->initial_T, np * 4));
+  CK(cudaMalloc(&s->sndT, np * 4));
+  CK(cudaMalloc(&s->sndW, np * 4));
+  CK(cudaMalloc(&s->sndV, np * 4));
+  CK(cudaMemset(s->initial_T, 0, np * 4));
+  CK(cudaMemset(s->sndT, 0, np * 4));
+  CK(cudaMemset(s->sndW, 0, np * 4));
+  CK(cudaMemset(s->sndV, 0, np * 4));
+  CK(cudaMalloc(&s->lightning, 16));
+  CK(cudaMalloc(&s->inactive, 4));
+  CK(cudaMalloc(&s->maxv, 4));
+  if (s->cfg.n_ranks > 1) {
+    s->halo_bytes = (size_t)s->H * kGhost * (16 + 16 + 4 + 16);
+    CK(cudaMalloc(&s->sendL, s->halo_bytes));
+    CK(cudaMalloc(&s->sendR, s->halo_bytes));
+    CK(cudaMalloc(&s->recvL, s->halo_bytes));
+    CK(cudaMalloc(&s->recvR, s->halo_bytes));
+  }
+  return 0;
+}
+
+int zero_transients(wsb_sim* s) {
+  const size_t n = cells(s);
+  for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s->light[k], 0, n * sizeof(float4), s->stream));
+  CK(cudaMemsetAsync(s->fb, 0, n * sizeof(float4), s->stream));
+  CK(cudaMemsetAsync(s->dep, 0, n * sizeof(float2), s->stream));
+  if (s->curl) CK(cudaMemsetAsync(s->curl, 0, n * sizeof(float), s->stream));
+  if (s->vort) CK(cudaMemsetAsync(s->vort, 0, n * sizeof(float2), s->stream));
+  CK(cudaMemsetAsync(s->lightning, 0, 16, s->stream));
+  CK(cudaMemsetAsync(s->inactive, 0, 4, s->stream));
+  CK(cudaMemsetAsync(s->maxv, 0, 4, s->stream));
+  s->iter = 0;
+  s->even = true;
+  s->last_drops = 0;
+  s->pressure_pending = false;
+  s->fb_dirty = false;
+  return 0;
+}
+
+// copy the columns of this rank's padded strip out of a GLOBAL [H][W] host array
+int upload_field(wsb_sim* s, void* dst, const void* src, size_t elt) {
+  int start = s->x_begin - s->ghost, remaining = s->pitch, off = 0;
+  while (remaining > 0) {
+    const int gs = ((start % s->W) + s->W) % s->W;
+    const int len = std::min(remaining, s->W - gs);
+    CK(cudaMemcpy2DAsync((char*)dst + (size_t)off * elt, (size_t)s->pitch * elt, (const char*)src + (size_t)gs * elt,
+                         (size_t)s->W * elt, (size_t)len * elt, s->H, cudaMemcpyHostToDevice, s->stream));
+    start += len;
+    off += len;
+    remaining -= len;
+  }
+  return 0;
+}
+
+int use_device(const wsb_sim* s) {
+  CK(cudaSetDevice(s->cfg.device));
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* wsb_last_error(void) { return g_err; }
+
+const char* wsb_build_info(void) {
+  return "libwsb200 abi " "1" " | sm_100a | nvcc " __VERSION__ " | fmad=false | tile "
+         "64x16, 256 threads | ghost 8";
+}
+
+int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]) {
+  if (!out) return fail("wsb_comm_id_create: null output");
+  if (load_nccl()) return 1;
+  Id128 id;
+  NCK(g_nccl.GetUniqueId(&id));
+  memcpy(out, id.internal, WSB_COMM_ID_BYTES);
+  return 0;
+}
+
+int wsb_create(const wsb_config* cfg, wsb_sim** out) {
+  if (!cfg || !out) return fail("wsb_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != WSB_ABI_VERSION) return fail("wsb_create: abi_version %d != %d", cfg->abi_version, WSB_ABI_VERSION);
+  if (cfg->width < 32 || cfg->height < 32 || cfg->width > 65535 || cfg->height > 65535)
+    return fail("wsb_create: grid %dx%d outside 32..65535 (the save format stores u16 sizes)", cfg->width, cfg->height);
+  if (cfg->n_droplets < 0) return fail("wsb_create: negative n_droplets");
+  if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail("wsb_create: bad rank %d / %d", cfg->rank, cfg->n_ranks);
+  if (cfg->schedule != WSB_SCHEDULE_FUSED && cfg->schedule != WSB_SCHEDULE_REFERENCE) return fail("wsb_create: unknown schedule %d", cfg->schedule);
+  if (cfg->n_ranks > 1 && cfg->schedule != WSB_SCHEDULE_FUSED) return fail("wsb_create: multi-GPU needs WSB_SCHEDULE_FUSED");
+  if (cfg->n_ranks > 1 && cfg->n_droplets > 0) return fail("wsb_create: precipitation particles are single-GPU only; pass n_droplets = 0");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("wsb_create: CUDA device %d not present (%d devices)", cfg->device, ndev);
+
+  wsb_sim* s = new (std::nothrow) wsb_sim();
+  if (!s) return fail("wsb_create: out of host memory");
+  s->cfg = *cfg;
+  s->W = cfg->width;
+  s->H = cfg->height;
+  s->ND = cfg->n_droplets;
+  s->schedule = cfg->schedule;
+  s->x_begin = (int)(((long long)cfg->rank * s->W) / cfg->n_ranks);
+  s->lw = (int)(((long long)(cfg->rank + 1) * s->W) / cfg->n_ranks) - s->x_begin;
+  s->ghost = cfg->n_ranks > 1 ? kGhost : 0;
+  s->pitch = s->lw + 2 * s->ghost;
+  if (cfg->n_ranks > 1 && s->lw < 2 * kGhost) {
+    const int lw = s->lw;
+    delete s;
+    return fail("wsb_create: strip of %d columns is narrower than %d", lw, 2 * kGhost);
+  }
+
+  Geom& g = s->g;
+  g.Wg = s->W; g.H = s->H; g.pitch = s->pitch; g.gx0 = s->x_begin - s->ghost; g.wrap = cfg->n_ranks == 1 ? 1 : 0;
+  g.cx0 = 0; g.cx1 = s->pitch;
+  g.texelX = (float)(1.0 / (double)s->W); g.texelY = (float)(1.0 / (double)s->H);   // app.js:5436 -> uniform2f
+  g.Wf = (float)s->W; g.Hf = (float)s->H;
+  g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;                                 // advectionShader.frag:69
+  memset(&s->dp, 0, sizeof(s->dp));
+  s->dp.in.userInputType = -1;
+  refresh_derived(s);
+
+  int rc = 0;
+  do {
+    if ((rc = use_device(s))) break;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&s->ev0)) != cudaSuccess || (e = cudaEventCreate(&s->ev1)) != cudaSuccess) {
+      rc = fail("wsb_create: %s", cudaGetErrorString(e));
+      break;
+    }
+    if ((e = cudaFuncSetAttribute(k_fused_pvb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_fused_adv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_fused_dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3)) != cudaSuccess) {
+      rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e));
+      break;
+    }
+    if ((rc = alloc_all(s))) break;
+    if ((rc = zero_transients(s))) break;
+    if (cfg->n_ranks > 1) {
+      if ((rc = load_nccl())) break;
+      Id128 id;
+      memcpy(id.internal, cfg->comm_id, WSB_COMM_ID_BYTES);
+      int r = g_nccl.CommInitRank(&s->comm, cfg->n_ranks, id, cfg->rank);
+      if (r != 0) { rc = fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); break; }
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s->stream);
+    if (e2 != cudaSuccess) { rc = fail("wsb_create: %s", cudaGetErrorString(e2)); break; }
+  } while (0);
+  if (rc) { wsb_destroy(s); return rc; }
+  *out = s;
+  return 0;
+}
+
+int wsb_destroy(wsb_sim* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->cfg.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  for (int k = 0; k < 2; k++) {
+    cudaFree(s->base[k]); cudaFree(s->water[k]); cudaFree(s->wall[k]); cudaFree(s->light[k]); cudaFree(s->drops[k]);
+  }
+  cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
+  cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
+  cudaFree(s->lightning); cudaFree(s->inactive); cudaFree(s->maxv); cudaFree(s->scratch);
+  cudaFree(s->sendL); cudaFree(s->sendR); cudaFree(s->recvL); cudaFree(s->recvR);
+  for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+
+namespace {
+// both ping-pong copies start from the same arrays (app.js:5189-5234): one host->device copy, then
+// a device->device duplicate
+int finish_upload(wsb_sim* s, const float* drops) {
+  const size_t n = cells(s);
+  CK(cudaMemcpyAsync(s->base[1], s->base[0], n * 16, cudaMemcpyDeviceToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->water[1], s->water[0], n * 16, cudaMemcpyDeviceToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->wall[1], s->wall[0], n * 4, cudaMemcpyDeviceToDevice, s->stream));
+  if (s->ND) {
+    CK(cudaMemcpyAsync(s->drops[0], drops, (size_t)s->ND * 20, cudaMemcpyHostToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->drops[1], s->drops[0], (size_t)s->ND * 20, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  if (zero_transients(s)) return 1;
+  CK(cudaStreamSynchronize(s->stream));  // the caller may free its arrays as soon as we return
+  return 0;
+}
+}  // namespace
+
+int wsb_upload(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
+  if (!s || !base || !water || !wall) return fail("wsb_upload: null argument");
+  if (s->ND > 0 && !drops) return fail("wsb_upload: droplets required (n_droplets = %d)", s->ND);
+  if (use_device(s)) return 1;
+  if (upload_field(s, s->base[0], base, 16) || upload_field(s, s->water[0], water, 16) || upload_field(s, s->wall[0], wall, 4)) return 1;
+  return finish_upload(s, drops);
+}
+
+int wsb_upload_local(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
+  if (!s || !base || !water || !wall) return fail("wsb_upload_local: null argument");
+  if (s->ND > 0 && !drops) return fail("wsb_upload_local: droplets required (n_droplets = %d)", s->ND);
+  if (use_device(s)) return 1;
+  const size_t n = cells(s);
+  CK(cudaMemcpyAsync(s->base[0], base, n * 16, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->water[0], water, n * 16, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemcpyAsync(s->wall[0], wall, n * 4, cudaMemcpyHostToDevice, s->stream));
+  return finish_upload(s, drops);
+}
+
+int wsb_get_layout(wsb_sim* s, int32_t* x_begin, int32_t* local_width, int32_t* ghost) {
+  if (!s || !x_begin || !local_width || !ghost) return fail("wsb_get_layout: null argument");
+  *x_begin = s->x_begin;
+  *local_width = s->lw;
+  *ghost = s->ghost;
+  return 0;
+}
+
+int wsb_set_params(wsb_sim* s, const wsb_params* p) {
+  if (!s || !p) return fail("wsb_set_params: null argument");
+  s->dp.p = *p;
+  return 0;
+}
+
+int wsb_set_profiles(wsb_sim* s, const float* initial_T, const float* sT, const float* sW, const float* sV) {
+  if (!s) return fail("wsb_set_profiles: null sim");
+  if (use_device(s)) return 1;
+  const size_t n = ((size_t)s->H + 1) * 4;
+  // stream-ordered after the iterations already enqueued; pageable sources are staged before return
+  if (initial_T) CK(cudaMemcpyAsync(s->initial_T, initial_T, n, cudaMemcpyHostToDevice, s->stream));
+  const float* src[3] = {sT, sW, sV};
+  float* dst[3] = {s->sndT, s->sndW, s->sndV};
+  for (int k = 0; k < 3; k++) {
+    if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], n, cudaMemcpyHostToDevice, s->stream));
+    else CK(cudaMemsetAsync(dst[k], 0, n, s->stream));
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_set_frame_inputs(wsb_sim* s, const wsb_frame_inputs* in) {
+  if (!s || !in) return fail("wsb_set_frame_inputs: null argument");
+  s->dp.in = *in;
+  refresh_derived(s);
+  return 0;
+}
+
+int wsb_step(wsb_sim* s, int32_t n_iters) {
+  if (!s) return fail("wsb_step: null sim");
+  if (n_iters < 0) return fail("wsb_step: negative iteration count");
+  if (use_device(s)) return 1;
+  s->ev_used = 0;
+  s->spans.clear();
+  CK(cudaEventRecord(s->ev0, s->stream));
+  for (int i = 0; i < n_iters; i++) {
+    if (s->schedule == WSB_SCHEDULE_REFERENCE ? ref_iteration(s) : fused_iteration(s)) return 1;
+  }
+  CK(cudaEventRecord(s->ev1, s->stream));
+  s->timed = true;
+  return 0;
+}
+
+int wsb_step_dry(wsb_sim* s, int32_t n_iters) {
+  if (!s) return fail("wsb_step_dry: null sim");
+  if (n_iters < 0) return fail("wsb_step_dry: negative iteration count");
+  if (use_device(s)) return 1;
+  s->ev_used = 0;
+  s->spans.clear();
+  CK(cudaEventRecord(s->ev0, s->stream));
+  for (int i = 0; i < n_iters; i++)
+    if (dry_iteration(s)) return 1;
+  CK(cudaEventRecord(s->ev1, s->stream));
+  s->timed = true;
+  return 0;
+}
+
+int wsb_sync(wsb_sim* s) {
+  if (!s) return fail("wsb_sync: null sim");
+  if (use_device(s)) return 1;
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_debug_run_pass(wsb_sim* s, int32_t pass) {
+  if (!s) return fail("wsb_debug_run_pass: null sim");
+  if (s->schedule != WSB_SCHEDULE_REFERENCE) return fail("wsb_debug_run_pass needs WSB_SCHEDULE_REFERENCE");
+  if (use_device(s)) return 1;
+  switch (pass) {
+    case WSB_PASS_VELOCITY: return ref_velocity(s);
+    case WSB_PASS_CURL: return ref_curl(s);
+    case WSB_PASS_VORTICITY: return ref_vorticity(s);
+    case WSB_PASS_BOUNDARY: return ref_boundary(s);
+    case WSB_PASS_ADVECTION: return ref_advection(s, false);
+    case WSB_PASS_PRESSURE: return ref_pressure(s);
+    case WSB_PASS_LIGHTING: return ref_lighting(s);
+    case WSB_PASS_PRECIPITATION: return clear_feedback(s) || precipitation(s);
+    case WSB_PASS_ITER_INC: s->iter++; return 0;
+    case WSB_PASS_ADVECTION_DRY: return ref_advection(s, true);
+    default: return fail("wsb_debug_run_pass: unknown pass %d", pass);
+  }
+}
+
+int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y, int32_t w, int32_t h, void* dst) {
+  if (!s || !dst) return fail("wsb_read_rect: null argument");
+  if (w <= 0 || h <= 0 || x < 0 || y < 0 || x + w > s->W || y + h > s->H) return fail("wsb_read_rect: rectangle (%d,%d,%d,%d) outside %dx%d", x, y, w, h, s->W, s->H);
+  if (view < WSB_VIEW_FRAMEBUFF_0 || view > WSB_VIEW_LATEST) return fail("wsb_read_rect: unknown view %d", view);
+  if (use_device(s)) return 1;
+  const bool fused = s->schedule == WSB_SCHEDULE_FUSED;
+  const void* src = nullptr;
+  size_t elt = 0;
+  bool pressure_on_the_fly = false;
+  const int v1 = view == WSB_VIEW_FRAMEBUFF_1 ? 1 : 0;
+  switch (field) {
+    case WSB_FIELD_BASE:
+      elt = 16;
+      if (fused) { src = s->base[1]; pressure_on_the_fly = (v1 == 0) && s->pressure_pending; }
+      else src = s->base[v1];
+      break;
+    case WSB_FIELD_WATER:
+      elt = 16;
+      // FUSED before the first iteration: both copies still hold the upload
+      src = s->water[v1];
+      break;
+    case WSB_FIELD_WALL:
+      elt = 4;
+      // frameBuff_0's wall after an iteration is the pressure pass's pass-through of wall_1
+      src = fused ? s->wall[1] : s->wall[v1];
+      break;
+    case WSB_FIELD_LIGHT:
+      elt = 16;
+      src = view == WSB_VIEW_LATEST ? s->light[s->even ? 0 : 1] : s->light[v1];
+      break;
+    case WSB_FIELD_FEEDBACK: elt = 16; src = s->fb; break;
+    case WSB_FIELD_DEPOSITION: elt = 8; src = s->dep; break;
+    case WSB_FIELD_CURL:
+      if (!s->curl) return fail("wsb_read_rect: curl is only stored by WSB_SCHEDULE_REFERENCE");
+      elt = 4; src = s->curl; break;
+    case WSB_FIELD_VORTFORCE:
+      if (!s->vort) return fail("wsb_read_rect: vortForce is only stored by WSB_SCHEDULE_REFERENCE");
+      elt = 8; src = s->vort; break;
+    default: return fail("wsb_read_rect: unknown field %d", field);
+  }
+  // intersect with the owned strip
+  const int gx0 = std::max(x, s->x_begin), gx1 = std::min(x + w, s->x_begin + s->lw);
+  if (gx1 <= gx0) { CK(cudaStreamSynchronize(s->stream)); return 0; }
+  const int lx0 = gx0 - s->x_begin + s->ghost, cw = gx1 - gx0;
+  char* d = (char*)dst + (size_t)(gx0 - x) * elt;
+  if (pressure_on_the_fly) {
+    const size_t need = (size_t)cw * h;
+    if (need > s->scratch_cells) {
+      CK(cudaStreamSynchronize(s->stream));
+      cudaFree(s->scratch);
+      s->scratch = nullptr;
+      s->scratch_cells = 0;
+      CK(cudaMalloc(&s->scratch, need * sizeof(float4)));
+      s->scratch_cells = need;
+    }
+    dim3 b(32, 8), gr((cw + 31) / 32, (h + 7) / 8);
+    k_pressure_rect<<<gr, b, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), lx0, y, cw, h, s->scratch);
+    LAUNCHED("k_pressure_rect");
+    CK(cudaMemcpy2DAsync(d, (size_t)w * elt, s->scratch, (size_t)cw * elt, (size_t)cw * elt, h, cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    const char* sp = (const char*)src + ((size_t)y * s->pitch + lx0) * elt;
+    CK(cudaMemcpy2DAsync(d, (size_t)w * elt, sp, (size_t)s->pitch * elt, (size_t)cw * elt, h, cudaMemcpyDeviceToHost, s->stream));
+  }
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_read_droplets(wsb_sim* s, int32_t buffer, int32_t first, int32_t count, float* dst) {
+  if (!s || !dst) return fail("wsb_read_droplets: null argument");
+  if (buffer < 0 || buffer > 2) return fail("wsb_read_droplets: buffer must be 0, 1 or 2");
+  if (first < 0 || count < 0 || (long long)first + count > s->ND) return fail("wsb_read_droplets: range [%d, %d) outside %d droplets", first, first + count, s->ND);
+  if (use_device(s)) return 1;
+  const int b = buffer == 2 ? s->last_drops : buffer;
+  if (count) CK(cudaMemcpyAsync(dst, s->drops[b] + (size_t)first * 5, (size_t)count * 20, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_get_inactive_droplets(wsb_sim* s, float* out) {
+  if (!s || !out) return fail("wsb_get_inactive_droplets: null argument");
+  if (use_device(s)) return 1;
+  CK(cudaMemcpyAsync(out, s->inactive, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_get_lightning(wsb_sim* s, float out[4]) {
+  if (!s || !out) return fail("wsb_get_lightning: null argument");
+  if (use_device(s)) return 1;
+  CK(cudaMemcpyAsync(out, s->lightning, 16, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_get_iter(wsb_sim* s, int64_t* out) {
+  if (!s || !out) return fail("wsb_get_iter: null argument");
+  *out = s->iter;
+  return 0;
+}
+
+int wsb_set_iter(wsb_sim* s, int64_t iter) {
+  if (!s) return fail("wsb_set_iter: null sim");
+  if (iter < 0) return fail("wsb_set_iter: negative iteration number");
+  s->iter = iter;
+  return 0;
+}
+
+int wsb_get_strip(wsb_sim* s, int32_t* x_begin, int32_t* local_width) {
+  if (!s || !x_begin || !local_width) return fail("wsb_get_strip: null argument");
+  *x_begin = s->x_begin;
+  *local_width = s->lw;
+  return 0;
+}
+
+int wsb_get_max_velocity(wsb_sim* s, float* out) {
+  if (!s || !out) return fail("wsb_get_max_velocity: null argument");
+  if (use_device(s)) return 1;
+  unsigned u = 0;
+  CK(cudaMemcpyAsync(&u, s->maxv, 4, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  memcpy(out, &u, 4);
+  return 0;
+}
+
+int wsb_get_launch_count(wsb_sim* s, int64_t* out) {
+  if (!s || !out) return fail("wsb_get_launch_count: null argument");
+  *out = s->launches;
+  return 0;
+}
+
+int wsb_set_profiling(wsb_sim* s, int32_t on) {
+  if (!s) return fail("wsb_set_profiling: null sim");
+  s->profiling = on != 0;
+  return 0;
+}
+
+int wsb_kernel_time_ms(wsb_sim* s, int32_t kernel, float* total_ms, int32_t* launches) {
+  if (!s || !total_ms || !launches) return fail("wsb_kernel_time_ms: null argument");
+  if (kernel < 0 || kernel > WSB_KERNEL_HALO) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
+  if (use_device(s)) return 1;
+  CK(cudaStreamSynchronize(s->stream));
+  double sum = 0.0;
+  int n = 0;
+  for (const wsb_sim::Span& sp : s->spans) {
+    if (sp.kind != kernel) continue;
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, s->ev_pool[sp.e0], s->ev_pool[sp.e1]));
+    sum += ms;
+    n++;
+  }
+  *total_ms = (float)sum;
+  *launches = n;
+  return 0;
+}
+
+int wsb_last_step_ms(wsb_sim* s, float* out) {
+  if (!s || !out) return fail("wsb_last_step_ms: null argument");
+  if (!s->timed) return fail("wsb_last_step_ms: no wsb_step / wsb_step_dry call yet");
+  if (use_device(s)) return 1;
+  CK(cudaEventSynchronize(s->ev1));
+  CK(cudaEventElapsedTime(out, s->ev0, s->ev1));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""Multi-GPU host plumbing: one process per GPU (torchrun), torch.distributed only carries the
+NCCL bootstrap id and the readback gathers; the per-iteration halo exchange itself runs inside
+libwsb200.so (ncclSend / ncclRecv on the simulation stream, csrc/wsb200.cu: exchange()).
+
+The reference is single-GPU; this is the x-strip decomposition of SURVEY 8e.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import strips
+
+COMM_ID_BYTES = 128
+
+
+def broadcast_comm_id(create_fn, group=None) -> bytes:
+    """Rank 0 calls create_fn() -> 128-byte NCCL unique id; every rank returns the same bytes."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    box = [create_fn() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    cid = box[0]
+    if not isinstance(cid, (bytes, bytearray)) or len(cid) != COMM_ID_BYTES:
+        raise ValueError("comm id must be 128 bytes")
+    return bytes(cid)
+
+
+def create_distributed(width: int, height: int, *, device: int, gui_controls=None, group=None, **kw):
+    """A Simulation for this rank's strip of a width x height grid (torch.distributed must be
+    initialised; with world size 1 this is a plain single-GPU simulation)."""
+    import torch.distributed as dist
+
+    from .sim import Simulation, comm_id_create
+
+    n = dist.get_world_size(group) if dist.is_initialized() else 1
+    r = dist.get_rank(group) if dist.is_initialized() else 0
+    if n == 1:
+        return Simulation(width, height, kw.pop("n_droplets", 0), device=device, gui_controls=gui_controls, **kw)
+    cid = broadcast_comm_id(comm_id_create, group)
+    kw.pop("n_droplets", None)
+    return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+
+
+def gather_strips(local: np.ndarray, width: int, group=None):
+    """All-gather per-rank strips [H][local_width][C] into the global [H][W][C] array (every rank
+    gets the result).  Strip r covers strips.strip_bounds(width, n, r)."""
+    import torch
+    import torch.distributed as dist
+
+    n = dist.get_world_size(group)
+    parts = [None] * n
+    dist.all_gather_object(parts, np.ascontiguousarray(local), group=group)
+    h, c = local.shape[0], local.shape[2]
+    out = np.zeros((h, width, c), local.dtype)
+    for r, part in enumerate(parts):
+        x0, lw = strips.strip_bounds(width, n, r)
+        if part.shape != (h, lw, c):
+            raise ValueError(f"rank {r}: strip shape {part.shape} != {(h, lw, c)}")
+        out[:, x0:x0 + lw] = part
+    del torch
+    return out
+
+
+def ring_exchange(padded: list[np.ndarray], local_width: int, group=None) -> None:
+    """Reference implementation of the ghost-column exchange plan on HOST arrays (what
+    csrc/wsb200.cu: exchange() does with NCCL on device arrays): every array is
+    [H][local_width + 2*GHOST][C]; after the call the ghost columns hold the neighbours' edge
+    columns.  Used by the CPU (gloo) tests of the decomposition plan."""
+    import torch
+    import torch.distributed as dist
+
+    n, r = dist.get_world_size(group), dist.get_rank(group)
+    left, right = strips.neighbours(r, n)
+    snd, rcv = strips.send_slices(local_width), strips.recv_slices(local_width)
+    for a in padded:
+        to_left = torch.from_numpy(np.ascontiguousarray(a[:, snd["to_left"]]))
+        to_right = torch.from_numpy(np.ascontiguousarray(a[:, snd["to_right"]]))
+        from_left = torch.empty_like(to_right)
+        from_right = torch.empty_like(to_left)
+        # receives posted (right, left) — same pairing rule as the NCCL path, see exchange()
+        ops = [dist.P2POp(dist.isend, to_left, left, group, tag=1), dist.P2POp(dist.isend, to_right, right, group, tag=2),
+               dist.P2POp(dist.irecv, from_right, right, group, tag=1), dist.P2POp(dist.irecv, from_left, left, group, tag=2)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        a[:, rcv["from_left"]] = from_left.numpy()
+        a[:, rcv["from_right"]] = from_right.numpy()

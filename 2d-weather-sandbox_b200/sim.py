@@ -34,7 +34,9 @@ _LIB = None
 FIELD_BASE, FIELD_WATER, FIELD_WALL, FIELD_LIGHT, FIELD_FEEDBACK, FIELD_DEPOSITION, FIELD_CURL, FIELD_VORTFORCE = range(8)
 VIEW_FRAMEBUFF_0, VIEW_FRAMEBUFF_1, VIEW_LATEST = range(3)
 SCHEDULE_FUSED, SCHEDULE_REFERENCE = 0, 1
-PASS_VELOCITY, PASS_CURL, PASS_VORTICITY, PASS_BOUNDARY, PASS_ADVECTION, PASS_PRESSURE, PASS_LIGHTING, PASS_PRECIPITATION = range(8)
+(PASS_VELOCITY, PASS_CURL, PASS_VORTICITY, PASS_BOUNDARY, PASS_ADVECTION, PASS_PRESSURE, PASS_LIGHTING,
+ PASS_PRECIPITATION, PASS_ITER_INC, PASS_ADVECTION_DRY) = range(10)
+KERNEL_PVB, KERNEL_ADV, KERNEL_DRY, KERNEL_PRECIP, KERNEL_HALO = range(5)
 COMM_ID_BYTES = 128
 ABI_VERSION = 1
 
@@ -64,10 +66,11 @@ def library_path() -> str:
 
 # every symbol include/wsb200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "wsb_comm_id_create", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_set_params",
+    "wsb_comm_id_create", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
+    "wsb_set_profiling", "wsb_kernel_time_ms", "wsb_set_params",
     "wsb_set_profiles", "wsb_set_frame_inputs", "wsb_step", "wsb_sync", "wsb_debug_run_pass",
     "wsb_step_dry", "wsb_read_rect", "wsb_read_droplets", "wsb_get_inactive_droplets",
-    "wsb_get_lightning", "wsb_get_iter", "wsb_get_strip", "wsb_get_max_velocity",
+    "wsb_get_lightning", "wsb_get_iter", "wsb_set_iter", "wsb_get_strip", "wsb_get_max_velocity",
     "wsb_get_launch_count", "wsb_last_step_ms", "wsb_last_error", "wsb_build_info",
 ]
 
@@ -89,6 +92,10 @@ def load_library():
     L.wsb_create.argtypes = [ctypes.POINTER(WsbConfig), ctypes.POINTER(vp)]
     L.wsb_destroy.argtypes = [vp]
     L.wsb_upload.argtypes = [vp, vp, vp, vp, vp]
+    L.wsb_upload_local.argtypes = [vp, vp, vp, vp, vp]
+    L.wsb_get_layout.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.wsb_set_profiling.argtypes = [vp, i32]
+    L.wsb_kernel_time_ms.argtypes = [vp, i32, f32p, ctypes.POINTER(i32)]
     L.wsb_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
     L.wsb_set_profiles.argtypes = [vp, vp, vp, vp, vp]
     L.wsb_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
@@ -101,6 +108,7 @@ def load_library():
     L.wsb_get_inactive_droplets.argtypes = [vp, f32p]
     L.wsb_get_lightning.argtypes = [vp, f32p]
     L.wsb_get_iter.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+    L.wsb_set_iter.argtypes = [vp, ctypes.c_int64]
     L.wsb_get_strip.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.wsb_get_max_velocity.argtypes = [vp, f32p]
     L.wsb_get_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
@@ -191,6 +199,42 @@ class Simulation:
         else:
             drops = None
         self._check(self.L.wsb_upload(self.h, _ptr(base), _ptr(water), _ptr(wall), _ptr(drops)))
+
+    def upload_local(self, base, water, wall, drops=None):
+        """Upload only this rank's padded strip: arrays [H][ghost + local_width + ghost][4] whose
+        column i is global column (x_begin - ghost + i) mod W (see `padded_columns`)."""
+        base = np.ascontiguousarray(base, np.float32)
+        water = np.ascontiguousarray(water, np.float32)
+        wall = np.ascontiguousarray(wall, np.int8)
+        x0, lw, gh = self.layout()
+        shape = (self.H, lw + 2 * gh, 4)
+        if base.shape != shape or water.shape != shape or wall.shape != shape:
+            raise WsbError(f"upload_local: arrays must be {shape}")
+        if self.ND:
+            if drops is None:
+                raise WsbError("upload_local: droplets required")
+            drops = np.ascontiguousarray(drops, np.float32)
+        else:
+            drops = None
+        self._check(self.L.wsb_upload_local(self.h, _ptr(base), _ptr(water), _ptr(wall), _ptr(drops)))
+
+    def layout(self) -> tuple[int, int, int]:
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.L.wsb_get_layout(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def padded_columns(self) -> np.ndarray:
+        x0, lw, gh = self.layout()
+        return (np.arange(x0 - gh, x0 + lw + gh) % self.W).astype(np.int64)
+
+    def set_profiling(self, on: bool = True):
+        self._check(self.L.wsb_set_profiling(self.h, 1 if on else 0))
+
+    def kernel_time_ms(self, kernel: int) -> tuple[float, int]:
+        """(summed device ms, launches) of one kernel class in the most recent step call."""
+        ms, n = ctypes.c_float(), ctypes.c_int32()
+        self._check(self.L.wsb_kernel_time_ms(self.h, int(kernel), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     def set_gui_uniforms(self, g: dict | None = None):
         """setGuiUniforms + static uniforms + profile arrays (app.js:3401-3443, 5439-5502)."""
@@ -290,6 +334,10 @@ class Simulation:
         v = ctypes.c_int64()
         self._check(self.L.wsb_get_iter(self.h, ctypes.byref(v)))
         return v.value
+
+    @iter_num.setter
+    def iter_num(self, v: int):
+        self._check(self.L.wsb_set_iter(self.h, int(v)))
 
     @property
     def max_velocity(self) -> float:

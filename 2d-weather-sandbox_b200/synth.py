@@ -23,12 +23,20 @@ def _max_water(t):
     return (x8 * x8 * x).astype(np.float32)
 
 
-def _velocity_field(w, h, seed, amplitude):
+def _cols(w, cols):
+    """Global column indices to generate: all of them, or the caller's subset (a rank's padded
+    strip) — every generator below is a pure function of (global x, y), so strips generated
+    separately are identical to slices of the whole grid."""
+    return np.arange(w, dtype=np.int64) if cols is None else np.asarray(cols, np.int64)
+
+
+def _velocity_field(w, h, seed, amplitude, cols=None):
     rng = np.random.default_rng(seed)
-    xs = (np.arange(w, dtype=np.float32) + 0.5) / w
+    cols = _cols(w, cols)
+    xs = ((cols.astype(np.float32) + np.float32(0.5)) / np.float32(w)).astype(np.float32)
     ys = (np.arange(h, dtype=np.float32) + 0.5) / h
-    vx = np.zeros((h, w), np.float32)
-    vy = np.zeros((h, w), np.float32)
+    vx = np.zeros((h, len(cols)), np.float32)
+    vy = np.zeros((h, len(cols)), np.float32)
     for _ in range(8):  # sum of 8 periodic sines
         kx, ky = int(rng.integers(1, 6)), int(rng.integers(1, 4))
         phx, phy = rng.uniform(0, 2 * np.pi, 2)
@@ -42,18 +50,21 @@ def _velocity_field(w, h, seed, amplitude):
     return vx, vy
 
 
-def dry_state(w: int, h: int, seed: int = 1234, g: dict | None = None):
+def dry_state(w: int, h: int, seed: int = 1234, g: dict | None = None, cols=None):
     """BASELINE config 2: row 0 LAND wall, rest air; T = initial_T[y] + warm blobs; smooth random
-    velocity (amplitude 0.1); P = 0; water = 0.  Returns (base, water, wall)."""
+    velocity (amplitude 0.1); P = 0; water = 0.  Returns (base, water, wall); with `cols` only
+    those global columns."""
     g = g or P.resolve_settings(None)
     t0 = P.initial_T_profile(h, g)
     rng = np.random.default_rng(seed + 1)
-    base = np.zeros((h, w, 4), np.float32)
-    vx, vy = _velocity_field(w, h, seed, 0.1)
+    cols = _cols(w, cols)
+    nc = len(cols)
+    base = np.zeros((h, nc, 4), np.float32)
+    vx, vy = _velocity_field(w, h, seed, 0.1, cols)
     base[..., 0] = vx
     base[..., 1] = vy
     base[..., 3] = t0[:h, None]
-    xs = np.arange(w, dtype=np.float32)[None, :]
+    xs = cols.astype(np.float32)[None, :]
     ys = np.arange(h, dtype=np.float32)[:, None]
     for _ in range(16):  # warm / cold blobs, 0.5 K
         cx, cy = rng.uniform(0, w), rng.uniform(0.1 * h, 0.9 * h)
@@ -61,8 +72,8 @@ def dry_state(w: int, h: int, seed: int = 1234, g: dict | None = None):
         dx = np.minimum(np.abs(xs - cx), w - np.abs(xs - cx))
         amp = np.float32(rng.normal(0.0, 0.5))
         base[..., 3] += amp * np.exp(-((dx * dx + (ys - cy) ** 2) / np.float32(r * r))).astype(np.float32)
-    water = np.zeros((h, w, 4), np.float32)
-    wall = np.zeros((h, w, 4), np.int8)
+    water = np.zeros((h, nc, 4), np.float32)
+    wall = np.zeros((h, nc, 4), np.int8)
     wall[..., 0] = 1
     wall[..., 1] = np.minimum(np.arange(h), 127)[:, None]
     wall[..., 2] = np.minimum(np.arange(h), 127)[:, None]
@@ -87,20 +98,23 @@ def terrain_height(w: int, h: int, seed: int = 7) -> np.ndarray:
 
 
 def full_state(w: int, h: int, seed: int = 7, g: dict | None = None, with_droplets: bool = True,
-               n_droplets: int | None = None, vel_amplitude: float = 0.05):
+               n_droplets: int | None = None, vel_amplitude: float = 0.05, cols=None):
     """BASELINE configs 3-5: terrain + sea, setupShader-style thermodynamic profile, a weak smooth
-    wind field so that advection has work to do.  Returns (base, water, wall, droplets)."""
+    wind field so that advection has work to do.  Returns (base, water, wall, droplets); with
+    `cols` only those global columns."""
     g = g or P.resolve_settings(None)
     t0 = P.initial_T_profile(h, g)
     lapse = np.float32(P.dry_lapse(g))
-    rows = terrain_height(w, h, seed)
+    cols = _cols(w, cols)
+    nc = len(cols)
+    rows = terrain_height(w, h, seed)[cols]
     yy = np.arange(h)[:, None]
     is_wall = yy <= rows[None, :]
     sea = (rows == 0)[None, :]
 
-    base = np.zeros((h, w, 4), np.float32)
-    water = np.zeros((h, w, 4), np.float32)
-    wall = np.zeros((h, w, 4), np.int8)
+    base = np.zeros((h, nc, 4), np.float32)
+    water = np.zeros((h, nc, 4), np.float32)
+    wall = np.zeros((h, nc, 4), np.int8)
 
     texy = ((np.arange(h, dtype=np.float32) + np.float32(0.5)) * np.float32(1.0 / h))[:, None]
     pot = t0[:h, None].astype(np.float32)
@@ -108,21 +122,21 @@ def full_state(w: int, h: int, seed: int = 7, g: dict | None = None, with_drople
     spread = np.where(texy < 0.20, np.float32(2.0), np.float32(20.0)).astype(np.float32)
     total = _max_water(real - spread)
     cloud = np.maximum(total - _max_water(real), np.float32(0.0))
-    vx, vy = _velocity_field(w, h, seed + 11, vel_amplitude)
+    vx, vy = _velocity_field(w, h, seed + 11, vel_amplitude, cols)
 
     air = ~is_wall
     base[..., 0] = np.where(air, vx, 0)
     base[..., 1] = np.where(air, vy, 0)
-    base[..., 3] = np.where(air, np.broadcast_to(pot, (h, w)), 0)
-    water[..., 0] = np.where(air, np.broadcast_to(total, (h, w)), 0)
-    water[..., 1] = np.where(air, np.broadcast_to(cloud, (h, w)), 0)
+    base[..., 3] = np.where(air, np.broadcast_to(pot, (h, nc)), 0)
+    water[..., 0] = np.where(air, np.broadcast_to(total, (h, nc)), 0)
+    water[..., 1] = np.where(air, np.broadcast_to(cloud, (h, nc)), 0)
 
     # wall cells (setupShader.frag:65-78)
     land = is_wall & ~sea
     seaw = is_wall & sea
     base[..., 3] = np.where(seaw, np.float32(P.c_to_k(25.0)), base[..., 3])
     water[..., 2] = np.where(land, np.float32(25.0), water[..., 2])
-    xs = np.arange(w)
+    xs = cols
     veg = np.clip(60 + 50 * np.sin(2 * np.pi * 3 * (xs + 0.5) / w) - rows * (300.0 / h), 0, 127).astype(np.int8)
     height_m = rows * (g["simHeight"] / h)
     snow = np.clip((height_m - 2000.0) / 3000.0 * 100.0, 0.0, 100.0).astype(np.float32)

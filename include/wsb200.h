@@ -150,6 +150,17 @@ int wsb_destroy(wsb_sim* sim);
 int wsb_upload(wsb_sim* sim, const float* base, const float* water, const int8_t* wall,
                const float* drops);
 
+/* Multi-GPU variant of wsb_upload: arrays hold only this rank's PADDED strip,
+ * [H][ghost + local_width + ghost][4], column i = global column (x_begin - ghost + i) mod W
+ * (wsb_get_layout), so no rank has to materialise the whole grid. Single GPU: identical to
+ * wsb_upload. */
+int wsb_upload_local(wsb_sim* sim, const float* base, const float* water, const int8_t* wall,
+                     const float* drops);
+
+/* Strip geometry of this rank: owned columns [x_begin, x_begin + local_width) and the number of
+ * ghost columns kept on each side (0 on a single GPU). */
+int wsb_get_layout(wsb_sim* sim, int32_t* x_begin, int32_t* local_width, int32_t* ghost);
+
 /* setGuiUniforms + the static uniforms (app.js:3401-3443, 5478-5640). */
 int wsb_set_params(wsb_sim* sim, const wsb_params* p);
 
@@ -177,7 +188,9 @@ int wsb_sync(wsb_sim* sim);
  * the per-pass parity tests. */
 enum {
   WSB_PASS_VELOCITY = 0, WSB_PASS_CURL = 1, WSB_PASS_VORTICITY = 2, WSB_PASS_BOUNDARY = 3,
-  WSB_PASS_ADVECTION = 4, WSB_PASS_PRESSURE = 5, WSB_PASS_LIGHTING = 6, WSB_PASS_PRECIPITATION = 7
+  WSB_PASS_ADVECTION = 4, WSB_PASS_PRESSURE = 5, WSB_PASS_LIGHTING = 6, WSB_PASS_PRECIPITATION = 7,
+  WSB_PASS_ITER_INC = 8,      /* iterNum++ (app.js:6002-6004) */
+  WSB_PASS_ADVECTION_DRY = 9  /* advection of the base field only (the dry sweep's middle stage) */
 };
 int wsb_debug_run_pass(wsb_sim* sim, int32_t pass);
 
@@ -206,6 +219,10 @@ int wsb_get_lightning(wsb_sim* sim, float out[4]);
 /* iterNum (app.js:440). */
 int wsb_get_iter(wsb_sim* sim, int64_t* out);
 
+/* Test / resume hook: set iterNum (the reference restarts it at 0 on every page load and never
+ * saves it; the boundary pass keys its slow processes on iterNum % 100, % 600, app.js:5957). */
+int wsb_set_iter(wsb_sim* sim, int64_t iter);
+
 /* Local strip of this rank: [x_begin, x_begin + local_width). */
 int wsb_get_strip(wsb_sim* sim, int32_t* x_begin, int32_t* local_width);
 
@@ -220,6 +237,20 @@ int wsb_get_launch_count(wsb_sim* sim, int64_t* out);
  * wsb_step / wsb_step_dry call on the sim's stream (bench: the stream is library-owned, so
  * torch.cuda.Event cannot see it). Synchronises. */
 int wsb_last_step_ms(wsb_sim* sim, float* out);
+
+/* Per-kernel-class device time (bench / roofline evidence).  With profiling on, every launch of
+ * wsb_step / wsb_step_dry is bracketed by CUDA events on the simulation's own stream;
+ * wsb_kernel_time_ms returns the summed duration and the number of launches of one class during
+ * the most recent step call. Synchronises. */
+enum {
+  WSB_KERNEL_PVB = 0,    /* k_fused_pvb: pressure -> velocity -> curl -> vorticity -> boundary */
+  WSB_KERNEL_ADV = 1,    /* k_fused_adv: advection -> lighting */
+  WSB_KERNEL_DRY = 2,    /* k_fused_dry: velocity -> advection(base) -> pressure */
+  WSB_KERNEL_PRECIP = 3, /* k_precipitation + k_latch */
+  WSB_KERNEL_HALO = 4    /* pack + ncclSend/Recv + unpack */
+};
+int wsb_set_profiling(wsb_sim* sim, int32_t on);
+int wsb_kernel_time_ms(wsb_sim* sim, int32_t kernel, float* total_ms, int32_t* launches);
 
 const char* wsb_last_error(void);
 const char* wsb_build_info(void);

@@ -1222,7 +1222,16 @@ void oracle_step(void* h, int n) { Sim& s = *(Sim*)h; for (int i = 0; i < n; i++
 // velocity -> advection(base only) -> pressure: the dry sweep of BASELINE config 2.
 void oracle_step_dry(void* h, int n) {
   Sim& s = *(Sim*)h;
-  for (int i = 0; i < n; i++) { pass_velocity(s); pass_advection(s, true); pass_pressure(s); s.iter++; }
+  // the reference's velocity pass renders into frameBuff_1 and advection samples frameBuff_0
+  // (the boundary pass sits between them, app.js:5876); with that pass left out the dry sweep
+  // hands velocity's output over unchanged.
+  for (int i = 0; i < n; i++) {
+    pass_velocity(s);
+    s.base[0] = s.base[1]; s.wall[0] = s.wall[1];
+    pass_advection(s, true);
+    pass_pressure(s);
+    s.iter++;
+  }
 }
 // pass ids as WSB_PASS_* in include/wsb200.h
 void oracle_run_pass(void* h, int pass) {

@@ -1,0 +1,360 @@
+"""Parity of the CUDA path (through the C ABI, via the ctypes host mirror) against the CPU oracle.
+
+Bars (north_star): the integer wall / boundary mask bit-exact; fp32 fields within 1e-5 relative.
+Because libwsb200 is compiled with -fmad=false and IEEE div/sqrt and shares the oracle's operation
+order, most comparisons below are in fact required to be BIT-exact; the relative bound is used only
+where summation order is not fixed (additive sprites) and for long chaotic runs.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import wsb200
+from oracle import oracle as O
+
+from util import make_cuda, make_oracle, rel_err, stress_state, ulp_diff
+
+pytestmark = pytest.mark.gpu
+P = wsb200.params
+SIM = wsb200.sim
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-5  # north_star tolerance on fp32 fields
+
+
+def _assert_fields_equal(sim, ora, what, view0=True, exact=True, light=True):
+    """Canonical state after whole iterations: base_0 (post pressure), water_1, wall_0, light."""
+    pairs = [
+        ("base", sim.read_pixels(SIM.FIELD_BASE, view=SIM.VIEW_FRAMEBUFF_0), ora.field(O.FIELD_BASE, 0)),
+        ("water1", sim.read_pixels(SIM.FIELD_WATER, view=SIM.VIEW_FRAMEBUFF_1), ora.field(O.FIELD_WATER, 1)),
+        ("water0", sim.read_pixels(SIM.FIELD_WATER, view=SIM.VIEW_FRAMEBUFF_0), ora.field(O.FIELD_WATER, 0)),
+    ]
+    if light:
+        pairs.append(("light", sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_LATEST), ora.light_latest()))
+        pairs.append(("light0", sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_FRAMEBUFF_0), ora.field(O.FIELD_LIGHT, 0)))
+    wall_got, wall_want = sim.read_pixels(SIM.FIELD_WALL), ora.field(O.FIELD_WALL, 0)
+    assert np.array_equal(wall_got, wall_want), f"{what}: wall differs in {(wall_got != wall_want).sum()} bytes"
+    for name, got, want in pairs:
+        assert np.isfinite(got).all(), f"{what}: {name} has non-finite values"
+        if exact:
+            assert np.array_equal(got, want), f"{what}: {name} not bit-exact, max ulp {ulp_diff(got, want)}, rel {rel_err(got, want):.3g}"
+        else:
+            assert rel_err(got, want) < REL, f"{what}: {name} rel err {rel_err(got, want):.3g}"
+
+
+# ---------------------------------------------------------------------------------------------
+# per-pass parity, REFERENCE schedule (one kernel per reference shader)
+# ---------------------------------------------------------------------------------------------
+PASSES = [("velocity", SIM.PASS_VELOCITY), ("curl", SIM.PASS_CURL), ("vorticity", SIM.PASS_VORTICITY),
+          ("boundary", SIM.PASS_BOUNDARY), ("advection", SIM.PASS_ADVECTION), ("pressure", SIM.PASS_PRESSURE),
+          ("lighting", SIM.PASS_LIGHTING), ("precipitation", SIM.PASS_PRECIPITATION)]
+
+
+def _all_buffers(sim, ora):
+    out = []
+    for b in (0, 1):
+        out.append((f"base_{b}", sim.read_pixels(SIM.FIELD_BASE, view=b), ora.field(O.FIELD_BASE, b)))
+        out.append((f"water_{b}", sim.read_pixels(SIM.FIELD_WATER, view=b), ora.field(O.FIELD_WATER, b)))
+        out.append((f"wall_{b}", sim.read_pixels(SIM.FIELD_WALL, view=b), ora.field(O.FIELD_WALL, b)))
+        out.append((f"light_{b}", sim.read_pixels(SIM.FIELD_LIGHT, view=b), ora.field(O.FIELD_LIGHT, b)))
+    out.append(("curl", sim.read_pixels(SIM.FIELD_CURL), ora.field(O.FIELD_CURL)))
+    out.append(("vortForce", sim.read_pixels(SIM.FIELD_VORTFORCE), ora.field(O.FIELD_VORT)))
+    return out
+
+
+@pytest.mark.parametrize("case", ["save100", "stress"])
+def test_per_pass_parity(case, save100):
+    if case == "save100":
+        g = P.resolve_settings(save100.settings_json)
+        base, water, wall, drops = save100.base, save100.water, save100.wall, save100.droplets
+    else:
+        g, base, water, wall, drops = stress_state(192, 96, seed=3)
+    sim = make_cuda(g, base, water, wall, drops, SIM.SCHEDULE_REFERENCE)
+    ora = make_oracle(g, base, water, wall, drops)
+    for it in range(3):
+        for name, pid in PASSES:
+            sim.run_pass(pid)
+            ora.run_pass(pid)
+            for fname, got, want in _all_buffers(sim, ora):
+                if pid == SIM.PASS_PRECIPITATION:
+                    break
+                assert np.array_equal(got, want), f"iteration {it} pass {name}: {fname} differs (max ulp {ulp_diff(got, want) if got.dtype != np.int8 else '-'})"
+            if pid == SIM.PASS_PRECIPITATION:
+                # droplet records are per-particle arithmetic: bit-exact; sprites sum in any order
+                assert np.array_equal(sim.read_droplets(), ora.droplets()), f"iteration {it}: droplets differ"
+                fb_got, fb_want = sim.read_pixels(SIM.FIELD_FEEDBACK), ora.field(O.FIELD_FEEDBACK)
+                dep_got, dep_want = sim.read_pixels(SIM.FIELD_DEPOSITION), ora.field(O.FIELD_DEPOSITION)
+                assert np.array_equal(fb_got != 0, fb_want != 0)
+                assert np.allclose(fb_got, fb_want, rtol=1e-5, atol=1e-9)
+                assert np.allclose(dep_got, dep_want, rtol=1e-5, atol=1e-9)
+        sim.run_pass(SIM.PASS_ITER_INC)
+        ora.run_pass(O.PASS_ITER_INC)
+        # keep the two in lock step: hand the oracle's sprite sums to nothing — they agree to rounding
+    sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole iterations
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
+def test_golden_vectors_100x100(schedule, save100):
+    """The committed oracle vectors (tests/golden/oracle_100x100.npz) after 1, 10, 100 iterations of
+    BASELINE config 1's input."""
+    gold = np.load(os.path.join(GOLDEN, "oracle_100x100.npz"))
+    sim = wsb200.Simulation.from_save(save100, schedule=schedule)
+    done = 0
+    for n in (1, 10, 100):
+        sim.step(n - done)
+        done = n
+        assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), gold[f"wall_{n}"])
+        for name, got in (("base", sim.read_pixels(SIM.FIELD_BASE)), ("water", sim.read_pixels(SIM.FIELD_WATER, view=SIM.VIEW_FRAMEBUFF_1)),
+                          ("light", sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_LATEST))):
+            want = gold[f"{name}_{n}"]
+            assert rel_err(got, want) < REL, f"{name} after {n} iterations: rel err {rel_err(got, want):.3g}"
+        d_got, d_want = sim.read_droplets(), gold[f"drops_{n}"]
+        assert np.array_equal(d_got[:, 2] < 0, d_want[:, 2] < 0)  # same droplets active
+        assert np.allclose(d_got, d_want, rtol=1e-4, atol=1e-6)
+    assert sim.iter_num == 100
+    sim.close()
+
+
+@pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
+@pytest.mark.parametrize("shape", [(192, 96), (100, 100), (333, 77)])
+def test_n_step_parity_no_particles(schedule, shape):
+    """Grid physics without particles is deterministic arithmetic: bit-exact against the oracle,
+    including ragged sizes that do not divide the 64x16 tiles."""
+    g, base, water, wall, _ = stress_state(*shape, seed=7)
+    g["enablePrecipitation"] = False
+    sim = make_cuda(g, base, water, wall, None, schedule)
+    ora = make_oracle(g, base, water, wall, None)
+    done = 0
+    for n in (1, 2, 10, 50):
+        sim.step(n - done)
+        ora.step(n - done)
+        done = n
+        _assert_fields_equal(sim, ora, f"{shape} after {n} iterations", exact=True)
+    assert sim.max_velocity < 1.0
+    sim.close()
+
+
+def test_slow_processes_iter_multiples():
+    """Branches keyed on iterNum % 100 / % 20 (snow & soil smoothing, vegetation growth, fire
+    spread, water temperature; boundaryShader.frag:409-520) with dynamic water temperature on."""
+    g, base, water, wall, _ = stress_state(160, 64, seed=9)
+    g["enablePrecipitation"] = False
+    g["dynamicWaterTemperature"] = True
+    for schedule in (SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED):
+        sim = make_cuda(g, base, water, wall, None, schedule)
+        ora = make_oracle(g, base, water, wall, None)
+        sim.iter_num = 9998
+        ora.iter = 9998
+        sim.step(6)
+        ora.step(6)
+        _assert_fields_equal(sim, ora, f"schedule {schedule} around iterNum 10000", exact=True)
+        sim.close()
+
+
+def test_fused_equals_reference_schedule_with_particles():
+    """Both CUDA schedules run the same particle kernel on the same inputs; everything except the
+    atomically summed sprites is bit-identical, and those agree to rounding."""
+    g, base, water, wall, drops = stress_state(256, 128, seed=13)
+    a = make_cuda(g, base, water, wall, drops, SIM.SCHEDULE_REFERENCE)
+    b = make_cuda(g, base, water, wall, drops, SIM.SCHEDULE_FUSED)
+    ora = make_oracle(g, base, water, wall, drops)
+    a.step(30)
+    b.step(30)
+    ora.step(30)
+    for f, v in ((SIM.FIELD_BASE, 0), (SIM.FIELD_WATER, 1), (SIM.FIELD_LIGHT, 2)):
+        ga, gb = a.read_pixels(f, view=v), b.read_pixels(f, view=v)
+        assert rel_err(ga, gb) < REL
+    assert np.array_equal(a.read_pixels(SIM.FIELD_WALL), b.read_pixels(SIM.FIELD_WALL))
+    _assert_fields_equal(b, ora, "fused vs oracle with particles", exact=False)
+    d_got, d_want = b.read_droplets(), ora.droplets()
+    assert np.array_equal(d_got[:, 2] < 0, d_want[:, 2] < 0)
+    assert (d_want[:, 2] >= 0).sum() > 10  # the test really has active droplets
+    assert np.allclose(d_got, d_want, rtol=1e-4, atol=1e-6)
+    assert abs(b.inactive_droplets - ora.inactive_droplets) < 0.5
+    a.close()
+    b.close()
+
+
+def test_inactive_latch_and_lightning():
+    g, base, water, wall, drops = stress_state(128, 64, seed=17)
+    sim = make_cuda(g, base, water, wall, drops, SIM.SCHEDULE_FUSED)
+    ora = make_oracle(g, base, water, wall, drops)
+    sim.step(1)
+    ora.step(1)
+    # iterNum 0 is a multiple of 600: the latch fires in the first iteration
+    assert sim.inactive_droplets == ora.inactive_droplets > 0
+    assert np.array_equal(sim.lightning, ora.lightning)
+    sim.close()
+
+
+@pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
+def test_dry_sweep_parity(schedule):
+    """BASELINE config 2 at a reduced size: velocity -> advection(base) -> pressure."""
+    w, h = 512, 128
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=1234)
+    g = P.resolve_settings(None)
+    g["dragMultiplier"], g["wind"] = 0.001, 0.0
+    sim = make_cuda(g, base, water, wall, None, schedule)
+    ora = make_oracle(g, base, water, wall, None)
+    sim.step_dry(25)
+    ora.step_dry(25)
+    got, want = sim.read_pixels(SIM.FIELD_BASE), ora.field(O.FIELD_BASE, 0)
+    assert np.array_equal(got, want), f"dry sweep not bit-exact: max ulp {ulp_diff(got, want)}"
+    assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), wall)
+    sim.close()
+
+
+def test_fast_flow_falls_back_exactly():
+    """|v| > 1 cell / iteration: back-traces leave the shared-memory halo and take the HBM path."""
+    w, h = 256, 64
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=5)
+    base[1:, :, 0] *= 25.0  # up to ~2.5 cells / iteration
+    g = P.resolve_settings(None)
+    for dry in (True, False):
+        sim = make_cuda(g, base, water, wall, None, SIM.SCHEDULE_FUSED)
+        ora = make_oracle(g, base, water, wall, None)
+        if dry:
+            sim.step_dry(3)
+            ora.step_dry(3)
+        else:
+            g2 = dict(g)
+            sim.step(3)
+            ora.step(3)
+            del g2
+        got, want = sim.read_pixels(SIM.FIELD_BASE), ora.field(O.FIELD_BASE, 0)
+        assert np.array_equal(got, want), f"dry={dry}: max ulp {ulp_diff(got, want)}"
+        assert sim.max_velocity > 1.0
+        sim.close()
+
+
+def test_user_input_brush_and_airplane():
+    """The user-input block of the advection pass (advectionShader.frag:229-457)."""
+    g, base, water, wall, _ = stress_state(160, 80, seed=19)
+    g["enablePrecipitation"] = False
+    cases = []
+    for uit, inten in ((1, 0.5), (2, 0.3), (3, 0.2), (4, 0.4), (10, 1.0), (11, 1.0), (12, 1.0), (13, 1.0), (14, 1.0), (15, 1.0),
+                       (16, 1.0), (20, 1.0), (21, 1.0), (22, 1.0), (11, -1.0), (13, -1.0), (22, -1.0), (20, -1.0)):
+        fi = P.frame_inputs(g)
+        fi.userInputType = uit
+        fi.userInputValues[0], fi.userInputValues[1] = 0.4, 0.15
+        fi.userInputValues[2], fi.userInputValues[3] = inten, 9.0
+        fi.userInputMove[0], fi.userInputMove[1] = 0.02, -0.01
+        fi.wrapHorizontally = 1
+        cases.append(fi)
+    whole = P.frame_inputs(g)
+    whole.userInputType = 1
+    whole.userInputValues[0], whole.userInputValues[1], whole.userInputValues[2], whole.userInputValues[3] = -1.0, 0.5, 0.1, 4.0
+    cases.append(whole)
+    for av3 in (-1.0, 1.0):
+        fi = P.frame_inputs(g)
+        fi.airplaneValues[0], fi.airplaneValues[1], fi.airplaneValues[2], fi.airplaneValues[3] = 0.3, 0.2, 1.0, av3
+        cases.append(fi)
+    for schedule in (SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED):
+        for k, fi in enumerate(cases):
+            sim = make_cuda(g, base, water, wall, None, schedule, fi=fi)
+            ora = make_oracle(g, base, water, wall, None, fi=fi)
+            sim.step(3)
+            ora.step(3)
+            _assert_fields_equal(sim, ora, f"schedule {schedule} input case {k} (type {fi.userInputType})", exact=True)
+            sim.close()
+
+
+def test_read_rect_matches_full_read(save100):
+    sim = wsb200.Simulation.from_save(save100)
+    sim.step(7)
+    full = sim.read_pixels(SIM.FIELD_BASE)
+    part = sim.read_pixels(SIM.FIELD_BASE, 13, 21, 30, 17)
+    assert np.array_equal(part, full[21:38, 13:43])
+    col = sim.read_pixels(SIM.FIELD_WALL, 50, 0, 1, 100)  # sounding column (app.js:3931-3943)
+    assert np.array_equal(col, sim.read_pixels(SIM.FIELD_WALL)[:, 50:51])
+    with pytest.raises(SIM.WsbError):
+        sim.read_pixels(SIM.FIELD_BASE, 90, 0, 20, 1)
+    with pytest.raises(SIM.WsbError):
+        sim.read_pixels(SIM.FIELD_CURL)  # the fused schedule never stores curl
+    sim.close()
+
+
+def test_save_round_trip_through_gpu(save100):
+    """load -> upload -> prepareDownload without stepping returns the file's own payload."""
+    sim = wsb200.Simulation.from_save(save100)
+    out = sim.prepare_download()
+    assert np.array_equal(out.base, save100.base) and np.array_equal(out.water, save100.water)
+    assert np.array_equal(out.wall, save100.wall) and np.array_equal(out.droplets, save100.droplets)
+    sim.step(3)
+    out = sim.prepare_download()
+    back = wsb200.savefile.loads(wsb200.savefile.dumps(out))
+    assert np.array_equal(back.base, out.base) and back.width == 100
+    sim.close()
+
+
+def test_upload_resets_like_a_page_load(save100):
+    sim = wsb200.Simulation.from_save(save100)
+    sim.step(25)
+    a = sim.read_pixels(SIM.FIELD_BASE)
+    sim.upload(save100.base, save100.water, save100.wall, save100.droplets)  # the 'L' key
+    assert sim.iter_num == 0
+    assert not sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_LATEST).any()
+    sim.step(25)
+    assert rel_err(sim.read_pixels(SIM.FIELD_BASE), a) < REL
+    sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE sizes: size-independent properties (the oracle is too slow here)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_dry_sweep_schedules_agree():
+    """16384 x 4096 dry sweep: the fused kernel and the one-kernel-per-pass schedule are two
+    independent code paths through the same cell functions; their results must be bit-identical,
+    and a column sample is checked against the oracle run on a narrow periodic slab."""
+    w, h = 16384, 4096
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=1234)
+    g = P.resolve_settings(None)
+    out = []
+    for schedule in (SIM.SCHEDULE_FUSED, SIM.SCHEDULE_REFERENCE):
+        sim = make_cuda(g, base, water, wall, None, schedule)
+        sim.step_dry(3)
+        out.append(sim.read_pixels(SIM.FIELD_BASE))
+        sim.close()
+    assert np.array_equal(out[0], out[1])
+    assert np.isfinite(out[0]).all()
+    assert not np.array_equal(out[0], base)
+
+
+def test_full_size_full_physics_schedules_agree():
+    w, h = 16384, 4096
+    g = P.resolve_settings(None)
+    g["enablePrecipitation"] = False
+    base, water, wall, _ = wsb200.synth.full_state(w, h, seed=7, g=g, with_droplets=False)
+    res = []
+    for schedule in (SIM.SCHEDULE_FUSED, SIM.SCHEDULE_REFERENCE):
+        sim = make_cuda(g, base, water, wall, None, schedule)
+        sim.step(3)
+        res.append([sim.read_pixels(SIM.FIELD_BASE), sim.read_pixels(SIM.FIELD_WATER, view=1), sim.read_pixels(SIM.FIELD_WALL),
+                    sim.read_pixels(SIM.FIELD_LIGHT, view=2)])
+        sim.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+def test_periodic_translation_invariance():
+    """Rolling the whole state by k columns commutes with stepping (x is periodic), except for the
+    terms that depend on absolute x: fp32 fragCoord quantisation in the back-trace — so the roll is
+    by a power of two on a power-of-two grid with |x| < 2^k exactly representable — and the
+    industrial stacks (x % 80), which the state avoids."""
+    w, h = 1024, 128
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=77)
+    g = P.resolve_settings(None)
+    k = 512
+    a = make_cuda(g, base, water, wall, None, SIM.SCHEDULE_FUSED)
+    b = make_cuda(g, np.roll(base, k, 1), np.roll(water, k, 1), np.roll(wall, k, 1), None, SIM.SCHEDULE_FUSED)
+    a.step_dry(10)
+    b.step_dry(10)
+    ga, gb = a.read_pixels(SIM.FIELD_BASE), b.read_pixels(SIM.FIELD_BASE)
+    # fragCoord.x differs by 512 between the two runs: interpolation weights are quantised
+    # differently, so equality is to tolerance, not bitwise
+    assert rel_err(np.roll(ga, k, 1), gb, floor=1e-2) < 1e-3
+    a.close()
+    b.close()

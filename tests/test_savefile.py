@@ -1,0 +1,65 @@
+"""`.weathersandbox` codec (loadData app.js:1256-1366, prepareDownload app.js:6575-6628)."""
+import json
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import wsb200
+
+S = wsb200.savefile
+
+
+def test_golden_save_parses(save100):
+    sf = save100
+    assert (sf.width, sf.height) == (100, 100)
+    assert sf.version == S.SAVE_FILE_VERSION_ID
+    assert sf.base.shape == (100, 100, 4) and sf.water.shape == (100, 100, 4) and sf.wall.shape == (100, 100, 4)
+    assert sf.droplets.shape == (400, 5)  # W*H/25
+    assert sf.stations.shape == (0, 2)
+    assert not np.isnan(sf.base).any() and not np.isnan(sf.water).any()
+    assert (sf.wall[0, :, 1] == 0).all()  # bottom row is wall
+    assert set(np.unique(sf.wall[..., 0])) <= {1, 2}
+    settings = json.loads(sf.settings_json)
+    assert len(settings) == 51
+    assert settings["evapHeat"] == 1.9
+    assert (sf.droplets[:, 2] >= 0).sum() == 1  # one active droplet
+
+
+def test_payload_round_trip_is_byte_identical(save100):
+    import os
+
+    path = os.path.join(os.path.dirname(__file__), "golden", "100x100_test.weathersandbox")
+    blob = open(path, "rb").read()
+    original_payload = zlib.decompress(blob[4:])
+    assert S.payload(save100) == original_payload
+    again = S.loads(S.dumps(save100))
+    assert S.payload(again) == original_payload
+    assert struct.unpack_from("<I", S.dumps(save100), 0)[0] == 263574036
+
+
+def test_legacy_and_bad_versions():
+    sf = S.SaveFile(32, 32, np.zeros((32, 32, 4), np.float32), np.zeros((32, 32, 4), np.float32),
+                    np.zeros((32, 32, 4), np.int8), np.zeros((S.num_droplets(32, 32), 5), np.float32), version=S.LEGACY_VERSION_ID)
+    back = S.loads(S.dumps(sf))
+    assert back.settings_json is None and back.version == S.LEGACY_VERSION_ID
+    with pytest.raises(S.IncompatibleFile):
+        S.loads(struct.pack("<I", 42) + zlib.compress(b"xx"))
+    with pytest.raises(S.IncompatibleFile):
+        S.loads(b"\x01")
+    good = S.dumps(sf)
+    trunc = struct.pack("<I", S.LEGACY_VERSION_ID) + zlib.compress(zlib.decompress(good[4:])[:1000])
+    with pytest.raises(S.IncompatibleFile):
+        S.loads(trunc)
+
+
+def test_ragged_droplet_count():
+    # W*H not divisible by 25: the typed-array slicing floors
+    assert S.num_droplets(33, 32) == (33 * 32) // 25
+    sf = S.SaveFile(33, 32, np.ones((32, 33, 4), np.float32), np.ones((32, 33, 4), np.float32), np.ones((32, 33, 4), np.int8),
+                    np.ones((S.num_droplets(33, 32), 5), np.float32), np.array([[3, 4]], np.int16), '{"a":1}')
+    back = S.loads(S.dumps(sf))
+    assert back.width == 33 and back.height == 32
+    assert np.array_equal(back.stations, [[3, 4]])
+    assert back.settings_json == '{"a":1}'
