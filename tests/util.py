@@ -14,6 +14,8 @@ def stress_state(w: int, h: int, seed: int = 3):
     sea + land terrain from synth.full_state, then urban / industrial / runway / fire / inert
     surface patches, snow, dry desert, smoke plumes, clouds, rain shafts, sub-zero air aloft."""
     g = P.resolve_settings(None)
+    g["dayNightCycle"] = False  # sun pinned (SURVEY 5.6): zenith angle from guiControls.sunAngle
+    g["sunAngle"] = 60.0
     base, water, wall, drops = wsb200.synth.full_state(w, h, seed=seed, g=g, vel_amplitude=0.3)
     rng = np.random.default_rng(seed)
     is_wall = wall[..., 1] == 0
@@ -77,8 +79,8 @@ def make_cuda(g, base, water, wall, drops, schedule, fi=None, **kw):
     h, w = base.shape[:2]
     sim = wsb200.Simulation(w, h, 0 if drops is None else drops.shape[0], schedule=schedule, gui_controls=g, **kw)
     sim.upload(base, water, wall, drops)
-    if fi is not None:
-        sim.set_frame_inputs(fi)
+    # same explicit per-frame uniforms as make_oracle (a day/night clock would recompute the angle)
+    sim.set_frame_inputs(fi if fi is not None else P.frame_inputs(g))
     return sim
 
 
