@@ -396,14 +396,15 @@ int dry_iteration(wsb_sim* s) {
     std::swap(s->wall[0], s->wall[1]);
     if (ref_advection(s, true) || ref_pressure(s)) return 1;
   } else {
-    // canonical FUSED state is base_1 with no pressure pending after a dry sweep
-    if (s->pressure_pending) return fail("wsb_step_dry after wsb_step is not supported on the FUSED schedule");
+    // same canonical state as the full fused schedule: base_1 = advection output, pressure pending
     {
       ProfScope prof(s, WSB_KERNEL_DRY);
-      k_fused_dry<<<tile_grid(s), kNT, kSmem3, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->base[0], s->maxv);
+      k_fused_dry<<<tile_grid(s), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->pressure_pending ? 1 : 0,
+                                                               s->base[0], s->maxv);
       LAUNCHED("k_fused_dry");
     }
     std::swap(s->base[0], s->base[1]);
+    s->pressure_pending = true;
     if (exchange(s, {{s->base[1], 16}})) return 1;
   }
   s->iter++;
@@ -512,6 +513,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
   if (cfg->abi_version != WSB_ABI_VERSION) return fail("wsb_create: abi_version %d != %d", cfg->abi_version, WSB_ABI_VERSION);
   if (cfg->width < 32 || cfg->height < 32 || cfg->width > 65535 || cfg->height > 65535)
     return fail("wsb_create: grid %dx%d outside 32..65535 (the save format stores u16 sizes)", cfg->width, cfg->height);
+  if ((long long)cfg->width * cfg->height > (1LL << 30)) return fail("wsb_create: more than 2^30 cells (32-bit cell indices)");
   if (cfg->n_droplets < 0) return fail("wsb_create: negative n_droplets");
   if (cfg->n_ranks < 1 || cfg->rank < 0 || cfg->rank >= cfg->n_ranks) return fail("wsb_create: bad rank %d / %d", cfg->rank, cfg->n_ranks);
   if (cfg->schedule != WSB_SCHEDULE_FUSED && cfg->schedule != WSB_SCHEDULE_REFERENCE) return fail("wsb_create: unknown schedule %d", cfg->schedule);
@@ -559,7 +561,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
     }
     if ((e = cudaFuncSetAttribute(k_fused_pvb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_fused_adv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_fused_dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem3)) != cudaSuccess) {
+        (e = cudaFuncSetAttribute(k_fused_dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDry)) != cudaSuccess) {
       rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e));
       break;
     }

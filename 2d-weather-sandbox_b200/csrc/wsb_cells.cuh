@@ -99,9 +99,11 @@ __device__ __forceinline__ void pressure_cell(float vx, float vy, float& P, floa
 
 // ---------------------------------------------------------------------------------------------
 // boundaryShader.frag:72-531
-//   Ctx: float bx/by/bt(x,y) of the post-velocity base; float4 base4(x,y); float4 water4(x,y);
-//        char4 wall4(x,y); float2 vort(x,y); float4 light4(x,y) (y clamped); float4 fb4(x,y);
-//        float2 dep2(x,y)
+//   Ctx is positioned at the cell and answers fetches by OFFSET (dx, dy in {-1,0,1}), so a tiled
+//   context turns them into compile-time-constant shared-memory offsets:
+//        float bx/by/bt(dx,dy) of the post-velocity base; float4 base4(dx,dy); float4 water4(dx,dy);
+//        char4 wall4(dx,dy); float2 vort(dx,dy); float4 light4(dx,dy) (y clamped); float4 fb4();
+//        float2 dep2()
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float calcEvaporation(const DevParams& d, float T, float W, float V, float M) {
   return gmax((maxWater(T) - W) * d.p.landEvaporation * (V / 127.0f + 0.1f) * gmin(M + 1.0f, 50.0f) * 0.05f, 0.0f);
@@ -115,13 +117,13 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
                               int x, int y, float4& base, float4& water, char4& wallOut) {
   const float texCoordY = ((float)y + 0.5f) * g.texelY;
   const float texCoordYp = texCoordY + g.texelY;
-  base = c.base4(x, y);
-  water = c.water4(x, y);
-  const float4 fb = c.fb4(x, y);
+  base = c.base4(0, 0);
+  water = c.water4(0, 0);
+  const float4 fb = c.fb4();
   const float realTemp = potentialToRealT(d, base.w, texCoordY);
-  const char4 w0 = c.wall4(x, y);
-  const char4 wXm = c.wall4(x - 1, y), wYm = c.wall4(x, y - 1), wXp = c.wall4(x + 1, y), wYp = c.wall4(x, y + 1);
-  const float4 light = c.light4(x, y);
+  const char4 w0 = c.wall4(0, 0);
+  const char4 wXm = c.wall4(-1, 0), wYm = c.wall4(0, -1), wXp = c.wall4(1, 0), wYp = c.wall4(0, 1);
+  const float4 light = c.light4(0, 0);
   int wType = w0.x, wDist = w0.y, wVert, wVeg = w0.w;
   bool nextToWall = false;
   wVert = (int)wYm.z + 1;  // :92
@@ -144,7 +146,7 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
 
     // gravity :132-148
     const float gravMult = 0.0001f;
-    const float TYp = c.bt(x, y + 1);
+    const float TYp = c.bt(0, 1);
     float gravityForce = ((base.w + TYp) * 0.5f - (initial_T[y] + initial_T[y + 1]) * 0.5f) * gravMult;
     gravityForce -= water.y * gravMult * d.p.waterWeight;
     gravityForce -= fb.x * gravMult * d.p.waterWeight;
@@ -154,7 +156,7 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
     if (wYm.y == 0) {  // :155
       nextToWall = true;
       wDist = 1;
-      float4 waterYm = c.water4(x, y - 1);
+      float4 waterYm = c.water4(0, -1);
       snowCover = waterYm.w;
       soilMoisture = waterYm.z;
       wVert = 1;
@@ -177,9 +179,9 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
 
     // vorticity confinement :201-208
     {
-      const float2 vf = c.vort(x, y);
-      const float2 vfXm = c.vort(x - 1, y);
-      const float2 vfYm = c.vort(x, y - 1);
+      const float2 vf = c.vort(0, 0);
+      const float2 vfXm = c.vort(-1, 0);
+      const float2 vfYm = c.vort(0, -1);
       float velocityFactor = glength(base.x, base.y) * 0.1f;
       float k = d.p.vorticity + velocityFactor;
       base.x += (vf.x + vfYm.x) * k;
@@ -228,13 +230,13 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
         base.x -= fabsf(base.x) * base.x * surfaceDrag * 50.0f;
       }
       const float exchangeRate = 0.015f;
-      if (wYp.z <= 5) base.x -= (base.x - c.bx(x, y + 1)) * exchangeRate;
-      if (wYm.z > 0) base.x -= (base.x - c.bx(x, y - 1)) * exchangeRate;
+      if (wYp.z <= 5) base.x -= (base.x - c.bx(0, 1)) * exchangeRate;
+      if (wYm.z > 0) base.x -= (base.x - c.bx(0, -1)) * exchangeRate;
     }
 
     if (wVert <= 8) {  // :305-372
       wVeg = wYm.w;
-      const float4 waterInSurface = c.water4(x, y - 1);
+      const float4 waterInSurface = c.water4(0, -1);
       const int t = wType;
       bool in = false;
       if (t == WALLTYPE_FIRE) {
@@ -277,7 +279,7 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
         }
       } else if (t == WALLTYPE_WATER) {
         if (wVert <= 1) {
-          float LocalWaterTemperature = c.bt(x, y - 1);
+          float LocalWaterTemperature = c.bt(0, -1);
           base.w += (LocalWaterTemperature - realTemp - 1.0f) / 1.0f * WSB_waterHeatExchangeRate;
           water.x += gmax((maxWater(LocalWaterTemperature) - water.x) * d.p.waterEvaporation / 1.0f, 0.0f);
         }
@@ -286,7 +288,7 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
   } else {  // wall :373
     wVert = (int)wYp.z - 1;
     if (wVert < 0) {  // :377
-      float4 wtYp = c.water4(x, y + 1);
+      float4 wtYp = c.water4(0, 1);
       water.z = wtYp.z;
       water.w = wtYp.w;
       wVeg = wYp.w;
@@ -294,13 +296,13 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
         if (wYp.x != WALLTYPE_WATER) {
           wType = wYp.x;
         } else if (wType == WALLTYPE_WATER) {
-          base.w = c.bt(x, y + 1);
+          base.w = c.bt(0, 1);
         }
       }
     } else if (wVert == 0) {  // surface layer :390
-      const float4 waterYp = c.water4(x, y + 1);
-      const float2 dep = c.dep2(x, y);
-      const float4 lightAbove = c.light4(x, y + 1);
+      const float4 waterYp = c.water4(0, 1);
+      const float2 dep = c.dep2();
+      const float4 lightAbove = c.light4(0, 1);
       const int t = wType;
       bool in = false;
       if (t == WALLTYPE_INDUSTRIAL) { in = true; wVeg = min(wVeg, 15); }
@@ -320,20 +322,20 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
       if (in || t == WALLTYPE_LAND) {  // :415-475
         water.z = gclamp(water.z + dep.x * 0.1f, 0.0f, 1000.0f);
         water.w = gclamp(water.w + dep.y * WSB_snowMassToHeight, 0.0f, 4000.0f);
-        const float TAbove = c.bt(x, y + 1);
+        const float TAbove = c.bt(0, 1);
         float realTempAboveSurface = potentialToRealT(d, TAbove, texCoordYp);
         float evaporation = calcEvaporation(d, realTempAboveSurface, waterYp.x, (float)wVeg, water.z) * 0.10f;
         water.z -= evaporation;
         if (d.iterI % 100 == 0) {
           float numNeighbors = 0.0f, totalNeighborSnow = 0.0f, totalNeighborSoilMoisture = 0.0f;
           if (wXm.z == 0 && (wXm.x == WALLTYPE_LAND || wXm.x == WALLTYPE_URBAN)) {
-            float4 wn = c.water4(x - 1, y);
+            float4 wn = c.water4(-1, 0);
             totalNeighborSnow += wn.w;
             totalNeighborSoilMoisture += wn.z;
             numNeighbors += 1.0f;
           }
           if (wXp.z == 0 && (wXp.x == WALLTYPE_LAND || wXp.x == WALLTYPE_URBAN)) {
-            float4 wn = c.water4(x + 1, y);
+            float4 wn = c.water4(1, 0);
             totalNeighborSnow += wn.w;
             totalNeighborSoilMoisture += wn.z;
             numNeighbors += 1.0f;
@@ -358,14 +360,14 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
         const float waterTempUpdateInterval = 20.0f;
         if (d.p.dynamicWaterTemperature >= 1.0f && gmod(d.iterNum, waterTempUpdateInterval) < 0.5f) {
           float numNeighbors = 0.0f, totalNeighborTemp = 0.0f;
-          if (wXm.x == WALLTYPE_WATER) { totalNeighborTemp += c.bt(x - 1, y); numNeighbors += 1.0f; }
-          if (wXp.x == WALLTYPE_WATER) { totalNeighborTemp += c.bt(x + 1, y); numNeighbors += 1.0f; }
+          if (wXm.x == WALLTYPE_WATER) { totalNeighborTemp += c.bt(-1, 0); numNeighbors += 1.0f; }
+          if (wXp.x == WALLTYPE_WATER) { totalNeighborTemp += c.bt(1, 0); numNeighbors += 1.0f; }
           if (numNeighbors > 0.0f) {
             float avgNeighborTemp = totalNeighborTemp / numNeighbors;
             base.w += (avgNeighborTemp - base.w) * 0.10f;
           }
           if (base.w > 500.0f) base.w = CtoK(25.0f);
-          float airTemperature = potentialToRealT(d, c.bt(x, y + 1), texCoordYp);
+          float airTemperature = potentialToRealT(d, c.bt(0, 1), texCoordYp);
           float netWaterHeating = 0.0f;
           netWaterHeating += (airTemperature - base.w) * WSB_waterHeatExchangeRate;
           netWaterHeating -= gmax((maxWater(base.w) - waterYp.x) * d.p.waterEvaporation, 0.0f) * d.p.evapHeat * 0.5f;
@@ -418,119 +420,89 @@ __device__ __forceinline__ float absHorizontalDist(float a, float b) {  // commo
   return gmin(gmin(fabsf(a - b), fabsf(1.0f + a - b)), 1.0f - a + b);
 }
 
-template <bool DRY, class C>
-__device__ void advection_cell(const C& c, const Geom& g, const DevParams& d, const float* __restrict__ initial_T,
-                               const float* __restrict__ sndT, const float* __restrict__ sndW,
-                               const float* __restrict__ sndV, int x, int y, float4& base, float4& water,
-                               char4& wallOut, float& vmaxOut) {
-  const int gx = global_x(g, x);
-  const float fragCoordX = (float)gx + 0.5f, fragCoordY = (float)y + 0.5f;
-  const float texCoordX = fragCoordX * g.texelX, texCoordY = fragCoordY * g.texelY;
-  const char4 w0 = c.wall4(x, y);
-  int wType = w0.x, wDist = w0.y, wVert = w0.z, wVeg = w0.w;
+// :85-89 velocities at the three staggered points of the cell
+struct AdvVel { float Px, Py, Vxx, Vxy, Vyx, Vyy; };
+__device__ __forceinline__ AdvVel adv_velocities(float vx00, float vy00, float vxXm, float vyYm, float vyXp, float vxYp,
+                                                 float vxXmYp, float vyXpYm) {
+  AdvVel a;
+  a.Px = (vxXm + vx00) / 2.0f;
+  a.Py = (vyYm + vy00) / 2.0f;
+  a.Vxx = vx00;
+  a.Vxy = (vyYm + vyXp + vy00 + vyXpYm) / 4.0f;
+  a.Vyx = (vxXm + vxYp + vxXmYp + vx00) / 4.0f;
+  a.Vyy = vy00;
+  return a;
+}
+
+// :111-187 air cell after the gathers: condensation / evaporation with latent heat, global
+// drying / heating / sounding forcing, clamp of total water
+__device__ __forceinline__ void adv_air_thermo(const Geom& g, const DevParams& d, const float* __restrict__ sndT,
+                                               const float* __restrict__ sndW, const float* __restrict__ sndV,
+                                               float texCoordY, float4& base, float4& water) {
   const wsb_params& p = d.p;
+  float realTemp = potentialToRealT(d, base.w, texCoordY);  // :111
+  float excessWater = water.x - maxWater(realTemp);         // :115
+  float overSaturation = excessWater - water.y;
+  float condensation;
+  if (overSaturation < 0.0f) condensation = overSaturation * 0.20f;
+  else condensation = overSaturation * p.condensationRate;
+  condensation = gmax(condensation, -water.y);
+  float dT = condensation * p.evapHeat * 1.0f;
+  base.w += dT;
+  realTemp += dT;
+  water.y += condensation;
+  if (texCoordY > p.globalEffectsStartAlt && texCoordY < p.globalEffectsEndAlt) {  // :154-181
+    water.x -= gclamp(p.globalDrying, 0.0f, gmax(water.x - maxWater(gmax(realTemp - 20.0f, CtoK(-80.0f))), 0.0f));
+    base.w += p.globalHeating;
+    int si = (int)(texCoordY * (1.0f / g.ltexelY));
+    int sm = max(si - 1, 0);
+    float Tdiff = base.w - (sndT[si] + sndT[sm]) / 2.0f;
+    base.w -= Tdiff * 0.001f * p.soundingForcing;
+    float Wdiff = water.x - (sndW[si] + sndW[sm]) / 2.0f;
+    water.x -= Wdiff * 0.001f * p.soundingForcing;
+    float dragK = 1.0f - map_rangeC(p.soundingForcing, 0.1f, 1.0f, 0.0f, 0.001f);
+    base.x *= dragK;
+    base.y *= dragK;
+    float velDiff = base.x - (sndV[si] + sndV[sm]) / 2.0f;
+    base.x -= velDiff * map_rangeC(p.soundingForcing, 0.9f, 1.0f, 0.0f, 0.001f);
+  }
+  water.x = gmax(water.x, 0.0f);  // :187
+}
 
-  if (wDist != 0) {  // not wall :73
-    const float vx00 = c.sbx(x, y), vy00 = c.sby(x, y);
-    const float vxXm = c.sbx(x - 1, y), vyYm = c.sby(x, y - 1);
-    const float vyXp = c.sby(x + 1, y), vxYp = c.sbx(x, y + 1);
-    const float vxXmYp = c.sbx(x - 1, y + 1), vyXpYm = c.sby(x + 1, y - 1);
-    vmaxOut = fmaxf(vmaxOut, fmaxf(fabsf(vx00), fabsf(vy00)));
-    // :85-89
-    const float velAtP_x = (vxXm + vx00) / 2.0f;
-    const float velAtP_y = (vyYm + vy00) / 2.0f;
-    const float velAtVx_x = vx00;
-    const float velAtVx_y = (vyYm + vyXp + vy00 + vyXpYm) / 4.0f;
-    const float velAtVy_x = (vxXm + vxYp + vxXmYp + vx00) / 4.0f;
-    const float velAtVy_y = vy00;
-
-    {  // base[VX] = bilerp(baseTex, fragCoord - velAtVx).x  :93
-      BilerpSetup b = bilerp_setup(fragCoordX - velAtVx_x, fragCoordY - velAtVx_y);
-      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
-      base.x = mix2d(c.bx(x0, y0), c.bx(x1, y0), c.bx(x0, y1), c.bx(x1, y1), b.fx, b.fx, b.fy);
-    }
-    {  // base[VY] = bilerp(baseTex, fragCoord - velAtVy).y  :94
-      BilerpSetup b = bilerp_setup(fragCoordX - velAtVy_x, fragCoordY - velAtVy_y);
-      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
-      base.y = mix2d(c.by(x0, y0), c.by(x1, y0), c.by(x0, y1), c.by(x1, y1), b.fx, b.fx, b.fy);
-    }
-    const float posPx = fragCoordX - velAtP_x, posPy = fragCoordY - velAtP_y;
-    {  // bilerpWall at the cell centre back-trace :96-99
-      BilerpSetup b = bilerp_setup(posPx, posPy);
-      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
-      WallMix m = wall_mix(c.wdist(x0, y0), c.wdist(x1, y0), c.wdist(x0, y1), c.wdist(x1, y1), b.fx, b.fy);
-      base.z = mix2d(c.bp(x0, y0), c.bp(x1, y0), c.bp(x0, y1), c.bp(x1, y1), m.ab, m.cd, m.abcd);
-      base.w = mix2d(c.bt(x0, y0), c.bt(x1, y0), c.bt(x0, y1), c.bt(x1, y1), m.ab, m.cd, m.abcd);
-      if (!DRY) {
-        water.x = mix2d(c.wt0(x0, y0), c.wt0(x1, y0), c.wt0(x0, y1), c.wt0(x1, y1), m.ab, m.cd, m.abcd);
-        water.y = mix2d(c.wt1(x0, y0), c.wt1(x1, y0), c.wt1(x0, y1), c.wt1(x1, y1), m.ab, m.cd, m.abcd);
-        water.w = mix2d(c.wt3(x0, y0), c.wt3(x1, y0), c.wt3(x0, y1), c.wt3(x1, y1), m.ab, m.cd, m.abcd);
+// :189-227 wall cell: base / water enter as the pass-through copies of this cell.
+// aboveDist / TAbove: wall distance and (pre-advection) temperature of the cell above.
+template <bool DRY>
+__device__ __forceinline__ void adv_wall_cell(const DevParams& d, float texCoordY, int wType, int aboveDist, float TAbove,
+                                              int& wVeg, float4& base, float4& water) {
+  if (wType == WALLTYPE_LAND) base.w = 1000.0f;
+  if (!DRY) {
+    wVeg = max(wVeg, 0);
+    water.z = gmax(water.z, 0.0f);
+    if (aboveDist != 0) {  // surface layer :207
+      float tempC = KtoC(potentialToRealT(d, TAbove, texCoordY));
+      if (water.w > 0.0f && tempC > 0.0f) {
+        float melting = gmin(tempC * WSB_snowMeltRate, water.w);
+        water.w -= melting;
+        base.w += melting / WSB_snowMassToHeight * d.p.meltingHeat;
+        water.z += melting;
       }
-    }
-    if (DRY) {
-      water = c.water4(x, y);
-    } else {
-      {  // precipitation visualisation, advected and pushed down :103
-        BilerpSetup b = bilerp_setup(posPx + 0.0f, posPy + 0.05f);
-        const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
-        WallMix m = wall_mix(c.wdist(x0, y0), c.wdist(x1, y0), c.wdist(x0, y1), c.wdist(x1, y1), b.fx, b.fy);
-        water.z = mix2d(c.wt2(x0, y0), c.wt2(x1, y0), c.wt2(x0, y1), c.wt2(x1, y1), m.ab, m.cd, m.abcd);
-      }
-      float realTemp = potentialToRealT(d, base.w, texCoordY);  // :111
-      float excessWater = water.x - maxWater(realTemp);         // :115
-      float overSaturation = excessWater - water.y;
-      float condensation;
-      if (overSaturation < 0.0f) condensation = overSaturation * 0.20f;
-      else condensation = overSaturation * p.condensationRate;
-      condensation = gmax(condensation, -water.y);
-      float dT = condensation * p.evapHeat * 1.0f;
-      base.w += dT;
-      realTemp += dT;
-      water.y += condensation;
-      if (texCoordY > p.globalEffectsStartAlt && texCoordY < p.globalEffectsEndAlt) {  // :154-181
-        water.x -= gclamp(p.globalDrying, 0.0f, gmax(water.x - maxWater(gmax(realTemp - 20.0f, CtoK(-80.0f))), 0.0f));
-        base.w += p.globalHeating;
-        int si = (int)(texCoordY * (1.0f / g.ltexelY));
-        int sm = max(si - 1, 0);
-        float Tdiff = base.w - (sndT[si] + sndT[sm]) / 2.0f;
-        base.w -= Tdiff * 0.001f * p.soundingForcing;
-        float Wdiff = water.x - (sndW[si] + sndW[sm]) / 2.0f;
-        water.x -= Wdiff * 0.001f * p.soundingForcing;
-        float dragK = 1.0f - map_rangeC(p.soundingForcing, 0.1f, 1.0f, 0.0f, 0.001f);
-        base.x *= dragK;
-        base.y *= dragK;
-        float velDiff = base.x - (sndV[si] + sndV[sm]) / 2.0f;
-        base.x -= velDiff * map_rangeC(p.soundingForcing, 0.9f, 1.0f, 0.0f, 0.001f);
-      }
-      water.x = gmax(water.x, 0.0f);  // :187
-    }
-  } else {  // wall :189
-    base = c.base4(x, y);
-    water = c.water4(x, y);
-    if (wType == WALLTYPE_LAND) base.w = 1000.0f;
-    if (!DRY) {
-      wVeg = max(wVeg, 0);
-      water.z = gmax(water.z, 0.0f);
-      if (c.swdist(x, y + 1) != 0) {  // surface layer :207
-        float tempC = KtoC(potentialToRealT(d, c.sbt(x, y + 1), texCoordY));
-        if (water.w > 0.0f && tempC > 0.0f) {
-          float melting = gmin(tempC * WSB_snowMeltRate, water.w);
-          water.w -= melting;
-          base.w += melting / WSB_snowMassToHeight * p.meltingHeat;
-          water.z += melting;
-        }
-        if (water.z > 0.0f && tempC > 0.0f) {
-          float evaporation = gmax((maxWater(CtoK(tempC)) - water.x) * 0.00001f, 0.0f);
-          water.z -= evaporation;
-        }
+      if (water.z > 0.0f && tempC > 0.0f) {
+        float evaporation = gmax((maxWater(CtoK(tempC)) - water.x) * 0.00001f, 0.0f);
+        water.z -= evaporation;
       }
     }
   }
+}
 
-  if (!DRY) {
-    // user input :229-401 (cold: only cells inside the brush do any work)
-    const float* uiv = d.in.userInputValues;
-    const int uit = d.in.userInputType;
+// :229-457 user input (brush), wall marker, airplane.  Inert for userInputType < 1 and
+// airplaneValues[3] in [0, 0.9] — the idle-frame values — in which case only the wall marker runs.
+__device__ __forceinline__ void adv_user_input(const Geom& g, const DevParams& d, const float* __restrict__ initial_T,
+                                               float texCoordX, float texCoordY, int aboveDist, int& wType, int& wDist,
+                                               int wVert, int& wVeg, float4& base, float4& water) {
+  const wsb_params& p = d.p;
+  const float* uiv = d.in.userInputValues;
+  const int uit = d.in.userInputType;
+  if (uit >= 1) {  // every branch below needs userInputType in {1,2,3,4} or >= 10
     bool inBrush = false;
     float weight = 1.0f;
     if (uiv[0] < -0.5f) {
@@ -560,7 +532,6 @@ __device__ void advection_cell(const C& c, const Geom& g, const DevParams& d, co
         base.x += d.in.userInputMove[0] * 5.0f * weight * intensity;
         if (!(uiv[0] < -0.5f)) base.y += d.in.userInputMove[1] * 5.0f * weight * intensity;
       } else if (uit >= 10) {
-        const int aboveDist = c.swdist(x, y + 1);
         if (intensity > 0.0f) {
           bool setWall = false;
           switch (uit) {
@@ -615,34 +586,94 @@ __device__ void advection_cell(const C& c, const Geom& g, const DevParams& d, co
         }
       }
     }
+  }
 
-    if (wDist == 0) water.x = (wType == WALLTYPE_WATER) ? 1002.0f : 1001.0f;  // :403-409
+  if (wDist == 0) water.x = (wType == WALLTYPE_WATER) ? 1002.0f : 1001.0f;  // :403-409
 
-    // airplane :415-457
-    const float* av = d.in.airplaneValues;
-    if (av[3] < 0.0f || av[3] > 0.9f) {  // the block only has an effect in these two cases
-      float px, py = av[1] - texCoordY;
-      if (d.in.wrapHorizontally) px = absHorizontalDist(av[0], texCoordX);
-      else px = fabsf(av[0] - texCoordX);
-      px *= g.ltexelY / g.ltexelX;
-      px *= g.Hf;
-      py *= g.Hf;
-      if (av[3] < 0.0f) { px += 0.0f; py += -1.0f; }
-      float distFromPlane = glength(px, py);
-      float planeInfluence = gmax(1.0f - distFromPlane, 0.0f) * 0.03f;
-      if (av[3] < 0.0f) water.z += planeInfluence * 100.0f;
-      if (av[3] > 0.9f && distFromPlane < 1.5f) {
-        if (wDist == 0) {
-          if (wType == WALLTYPE_LAND && wVert == 0) wType = WALLTYPE_FIRE;
-        } else {
-          base.z += 0.05f;
-          base.w = CtoK(50.0f);
-          water.x += 1.0f;
-          water.w += 10.0f;
-        }
+  // airplane :415-457
+  const float* av = d.in.airplaneValues;
+  if (av[3] < 0.0f || av[3] > 0.9f) {  // the block only has an effect in these two cases
+    float px, py = av[1] - texCoordY;
+    if (d.in.wrapHorizontally) px = absHorizontalDist(av[0], texCoordX);
+    else px = fabsf(av[0] - texCoordX);
+    px *= g.ltexelY / g.ltexelX;
+    px *= g.Hf;
+    py *= g.Hf;
+    if (av[3] < 0.0f) { px += 0.0f; py += -1.0f; }
+    float distFromPlane = glength(px, py);
+    float planeInfluence = gmax(1.0f - distFromPlane, 0.0f) * 0.03f;
+    if (av[3] < 0.0f) water.z += planeInfluence * 100.0f;
+    if (av[3] > 0.9f && distFromPlane < 1.5f) {
+      if (wDist == 0) {
+        if (wType == WALLTYPE_LAND && wVert == 0) wType = WALLTYPE_FIRE;
+      } else {
+        base.z += 0.05f;
+        base.w = CtoK(50.0f);
+        water.x += 1.0f;
+        water.w += 10.0f;
       }
     }
   }
+}
+
+// Generic form: every fetch goes through the context (global memory with wrap, or a checked tile).
+template <bool DRY, class C>
+__device__ void advection_cell(const C& c, const Geom& g, const DevParams& d, const float* __restrict__ initial_T,
+                               const float* __restrict__ sndT, const float* __restrict__ sndW,
+                               const float* __restrict__ sndV, int x, int y, float4& base, float4& water,
+                               char4& wallOut, float& vmaxOut) {
+  const int gx = global_x(g, x);
+  const float fragCoordX = (float)gx + 0.5f, fragCoordY = (float)y + 0.5f;
+  const float texCoordX = fragCoordX * g.texelX, texCoordY = fragCoordY * g.texelY;
+  const char4 w0 = c.wall4(x, y);
+  int wType = w0.x, wDist = w0.y, wVert = w0.z, wVeg = w0.w;
+  const int aboveDist = c.swdist(x, y + 1);
+
+  if (wDist != 0) {  // not wall :73
+    const float vx00 = c.sbx(x, y), vy00 = c.sby(x, y);
+    vmaxOut = fmaxf(vmaxOut, fmaxf(fabsf(vx00), fabsf(vy00)));
+    const AdvVel a = adv_velocities(vx00, vy00, c.sbx(x - 1, y), c.sby(x, y - 1), c.sby(x + 1, y), c.sbx(x, y + 1),
+                                    c.sbx(x - 1, y + 1), c.sby(x + 1, y - 1));
+    {  // base[VX] = bilerp(baseTex, fragCoord - velAtVx).x  :93
+      BilerpSetup b = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
+      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
+      base.x = mix2d(c.bx(x0, y0), c.bx(x1, y0), c.bx(x0, y1), c.bx(x1, y1), b.fx, b.fx, b.fy);
+    }
+    {  // base[VY] = bilerp(baseTex, fragCoord - velAtVy).y  :94
+      BilerpSetup b = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
+      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
+      base.y = mix2d(c.by(x0, y0), c.by(x1, y0), c.by(x0, y1), c.by(x1, y1), b.fx, b.fx, b.fy);
+    }
+    const float posPx = fragCoordX - a.Px, posPy = fragCoordY - a.Py;
+    {  // bilerpWall at the cell centre back-trace :96-99
+      BilerpSetup b = bilerp_setup(posPx, posPy);
+      const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
+      WallMix m = wall_mix(c.wdist(x0, y0), c.wdist(x1, y0), c.wdist(x0, y1), c.wdist(x1, y1), b.fx, b.fy);
+      base.z = mix2d(c.bp(x0, y0), c.bp(x1, y0), c.bp(x0, y1), c.bp(x1, y1), m.ab, m.cd, m.abcd);
+      base.w = mix2d(c.bt(x0, y0), c.bt(x1, y0), c.bt(x0, y1), c.bt(x1, y1), m.ab, m.cd, m.abcd);
+      if (!DRY) {
+        water.x = mix2d(c.wt0(x0, y0), c.wt0(x1, y0), c.wt0(x0, y1), c.wt0(x1, y1), m.ab, m.cd, m.abcd);
+        water.y = mix2d(c.wt1(x0, y0), c.wt1(x1, y0), c.wt1(x0, y1), c.wt1(x1, y1), m.ab, m.cd, m.abcd);
+        water.w = mix2d(c.wt3(x0, y0), c.wt3(x1, y0), c.wt3(x0, y1), c.wt3(x1, y1), m.ab, m.cd, m.abcd);
+      }
+    }
+    if (DRY) {
+      water = c.water4(x, y);
+    } else {
+      {  // precipitation visualisation, advected and pushed down :103
+        BilerpSetup b = bilerp_setup(posPx + 0.0f, posPy + 0.05f);
+        const int x0 = x + (b.ix - gx), x1 = x0 + 1, y0 = b.iy, y1 = b.iy + 1;
+        WallMix m = wall_mix(c.wdist(x0, y0), c.wdist(x1, y0), c.wdist(x0, y1), c.wdist(x1, y1), b.fx, b.fy);
+        water.z = mix2d(c.wt2(x0, y0), c.wt2(x1, y0), c.wt2(x0, y1), c.wt2(x1, y1), m.ab, m.cd, m.abcd);
+      }
+      adv_air_thermo(g, d, sndT, sndW, sndV, texCoordY, base, water);
+    }
+  } else {  // wall :189
+    base = c.base4(x, y);
+    water = c.water4(x, y);
+    adv_wall_cell<DRY>(d, texCoordY, wType, aboveDist, c.sbt(x, y + 1), wVeg, base, water);
+  }
+  if (!DRY) adv_user_input(g, d, initial_T, texCoordX, texCoordY, aboveDist, wType, wDist, wVert, wVeg, base, water);
   wallOut = pack_wall(wType, wDist, wVert, wVeg);
 }
 

@@ -2,24 +2,31 @@
 // stencil kernels (+ the particle kernel), and the fused "dry sweep".
 //
 //   k_fused_pvb   pressure(prev iteration) -> velocity -> curl -> vorticity -> boundary
-//                 reads  base_1, wall_1 (tile + 3-cell halo, staged in shared memory as SoA planes),
-//                        water_1, light_0, feedback, deposition (own cell, sparse neighbours)
+//                 reads  base_1, wall_1 (tile + 3-cell halo, cp.async into shared memory),
+//                        water_1, light_0 (own cell, prefetched; sparse neighbours), feedback,
+//                        deposition (only after a particle pass)
 //                 writes base_0, water_0, wall_0                      88 (+24) B / cell
 //   k_fused_adv   advection (+ condensation, forcing, wall cells, brush, airplane) -> lighting
-//                 reads  base_0, water_0, wall_0 (tile + 2-cell halo in shared memory), light_src
+//                 reads  base_0, water_0, wall_0, light_src (tile + 2-cell halo, cp.async)
 //                 writes base_1, water_1, wall_1, light_dst           104 B / cell
-//   k_fused_dry   velocity -> advection(base only) -> pressure        36 B / cell
+//   k_fused_dry   pressure(prev iteration) -> velocity -> advection(base only)   36 B / cell
 //
 // The reference's pressure pass (last grid pass of iteration i) is folded into the first kernel of
 // iteration i+1, so base "after pressure" never travels through HBM; wsb_read_rect materialises it
 // on demand for the rectangle being read.  curl and vortForce never leave shared memory.
 //
-// Tiles are loaded with coalesced 16-byte loads (one float4 cell per lane, 512 B per warp) and
-// transposed into per-channel planes so that the stencil and the bilinear back-trace gathers read
-// 4-byte words from conflict-free consecutive banks instead of 16-byte AoS cells (4x less
-// shared-memory traffic on the channel-granular gathers).  TMA is deliberately not used: a
-// tensor-map box lands in shared memory in the AoS layout and cannot apply the periodic wrap at
-// the domain edge; see DESIGN.md.
+// Staging: every thread issues cp.async (LDGSTS) copies for its share of the tile + halo —
+// 8-byte pieces of the 16-byte AoS cells, so the tile lands in shared memory already split into
+// (vx,vy) / (P,T) / (total,cloud) float2 planes and scalar planes — then one wait + barrier.  All
+// of a CTA's HBM reads are in flight at once and no register is spent on staging.  The periodic
+// wrap of the reference's REPEAT textures only exists on edge tiles (a block-uniform branch).
+// Stencil passes then sweep the staged planes in place; the final per-cell pass gathers with
+// plain shared-memory indices.  A back-trace that leaves the halo (|v| >= 1 cell / iteration, never
+// seen in the shipped saves) takes an exact, slow global-memory path.
+//
+// TMA (cp.async.bulk.tensor) is deliberately not used: a tensor-map box lands in shared memory in
+// the AoS global layout (the gathers want channel planes: 4x fewer shared-memory wavefronts) and
+// cannot apply the periodic wrap at the domain edge; see DESIGN.md.
 #pragma once
 #include "wsb_cells.cuh"
 #include "wsb_ref_kernels.cuh"
@@ -28,330 +35,86 @@ namespace wsb {
 
 constexpr int kTX = 64;   // tile width  (cells) — 2 warps wide, 1 KiB of float4 per row
 constexpr int kTY = 16;   // tile height (cells)
-constexpr int kNT = 256;  // threads per CTA
+constexpr int kNT = 256;  // threads per CTA: thread (tx, ty0) computes rows ty0, ty0+4, ty0+8, ty0+12
+constexpr int kRowStep = kNT / kTX;
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_pvb
+// cp.async (LDGSTS) helpers
 // ---------------------------------------------------------------------------------------------
-constexpr int kH1 = 3;                      // halo of the pressure->boundary chain
-constexpr int kSW1 = kTX + 2 * kH1;         // 70
-constexpr int kSH1 = kTY + 2 * kH1;         // 22
-constexpr int kN1 = kSW1 * kSH1;            // 1540 cells per staged tile
-constexpr size_t kSmem1 = (size_t)kN1 * 4 * 8;  // vx vy P T(/curl) T2 wall vfx vfy
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* s, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-struct PvbCtx {  // boundary_cell context: base / wall / vortForce from the tile, the rest from HBM
-  const float *sVX, *sVY, *sP, *sT2, *sVFX, *sVFY;
-  const int* sWall;
-  int X0, Y0;  // cell coordinates of tile-region element (0,0)
-  GlobalCtx glob;
-  // feedback / deposition are read AND cleared by this kernel (own cell only): plain pointers,
-  // not the read-only path.  useFb = 0: both targets are known to be all zero, skip the reads.
-  const float4* fbp;
-  const float2* depp;
-  int useFb;
-  __device__ __forceinline__ int si(int x, int y) const { return (y - Y0) * kSW1 + (x - X0); }
-  __device__ __forceinline__ float4 base4(int x, int y) const { int s = si(x, y); return make_float4(sVX[s], sVY[s], sP[s], sT2[s]); }
-  __device__ __forceinline__ float bx(int x, int y) const { return sVX[si(x, y)]; }
-  __device__ __forceinline__ float by(int x, int y) const { return sVY[si(x, y)]; }
-  __device__ __forceinline__ float bt(int x, int y) const { return sT2[si(x, y)]; }
-  __device__ __forceinline__ char4 wall4(int x, int y) const {
-    int v = sWall[si(x, y)];
-    return *reinterpret_cast<char4*>(&v);
-  }
-  __device__ __forceinline__ float2 vort(int x, int y) const { int s = si(x, y); return make_float2(sVFX[s], sVFY[s]); }
-  __device__ __forceinline__ float4 water4(int x, int y) const { return glob.water4(x, y); }
-  __device__ __forceinline__ float4 light4(int x, int y) const { return glob.light4(x, y); }
-  __device__ __forceinline__ float4 fb4(int x, int y) const {
-    return useFb ? fbp[glob.idx(x, y)] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __device__ __forceinline__ float2 dep2(int x, int y) const { return useFb ? depp[glob.idx(x, y)] : make_float2(0.f, 0.f); }
-};
+__device__ __forceinline__ char4 as_char4(int w) { return *reinterpret_cast<const char4*>(&w); }
 
-// glob: base = base_1, wall = wall_1, water = water_1, light = light_0 (glob.fb / glob.dep unused).
-// useFb: feedback / deposition hold data from the last particle pass; the kernel consumes them and
-// writes the zeros of the reference's gl.clear (app.js:5933-5934) back to the cells that were hit.
-__global__ void __launch_bounds__(kNT) k_fused_pvb(GlobalCtx glob, DevParams d, const float* __restrict__ initial_T,
-                                                   int applyPressure, int useFb, float4* fb, float2* dep,
-                                                   float4* __restrict__ baseOut, float4* __restrict__ waterOut,
-                                                   char4* __restrict__ wallOut) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kN1;
-  float* sP = sVY + kN1;
-  float* sT = sP + kN1;    // pre-pressure T, later reused for curl
-  float* sT2 = sT + kN1;   // post-pressure T
-  int* sWall = reinterpret_cast<int*>(sT2 + kN1);
-  float* sVFX = reinterpret_cast<float*>(sWall + kN1);
-  float* sVFY = sVFX + kN1;
-  float* sCurl = sT;
-
-  const Geom& g = glob.g;
+// Visit every cell of the staged region [X0, X0+SW) x [Y0, Y0+SH): f(s, ci, cil) with s the
+// shared-memory index, ci the global cell index (periodic wrap) and cil the global cell index for
+// the light texture (wrap S = REPEAT, wrap T = CLAMP_TO_EDGE, app.js:5276-5279).
+template <int SW, int SH, class F>
+__device__ __forceinline__ void for_each_staged(const Geom& g, int X0, int Y0, F&& f) {
+  constexpr int N = SW * SH;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kH1, Y0 = blockIdx.y * kTY - kH1;
-
-  // S0: stage base_1 / wall_1 tile + halo (periodic wrap) as SoA planes
-  for (int s = tid; s < kN1; s += kNT) {
-    const int j = s / kSW1, i = s - j * kSW1;
-    const size_t ci = (size_t)wrap_y(Y0 + j, g.H) * g.pitch + wrap_x(g, X0 + i);
-    const float4 b = glob.base[ci];
-    sVX[s] = b.x; sVY[s] = b.y; sP[s] = b.z; sT[s] = b.w;
-    sWall[s] = reinterpret_cast<const int*>(glob.wall)[ci];
-  }
-  __syncthreads();
-
-  // S1: pressure pass of the previous iteration (pressureShader.frag), valid for i,j >= 1
-  for (int s = tid; s < kN1; s += kNT) {
-    const int j = s / kSW1, i = s - j * kSW1;
-    float P = sP[s], T = sT[s];
-    if (applyPressure && i >= 1 && j >= 1) {
-      const int wv = sWall[s - kSW1];
-      const char4 wYm = *reinterpret_cast<const char4*>(&wv);
-      pressure_cell(sVX[s], sVY[s], P, T, sVX[s - 1], sVY[s - kSW1], sT[s - kSW1], wYm.x, wYm.y);
+  const bool interior = (X0 >= 0) && (X0 + SW <= g.pitch) && (Y0 >= 0) && (Y0 + SH <= g.H);
+  if (interior) {  // block-uniform: no wrap, incremental (row, column) walk without divisions
+    constexpr int DJ = kNT / SW, DI = kNT % SW;
+    int i = tid % SW;
+    int ci = (Y0 + tid / SW) * g.pitch + X0 + i;
+    const int stepA = DJ * g.pitch + DI, stepB = g.pitch - SW;
+#pragma unroll
+    for (int s = tid; s < N; s += kNT) {
+      f(s, ci, ci);
+      i += DI;
+      ci += stepA;
+      if (i >= SW) { i -= SW; ci += stepB; }
     }
-    sP[s] = P;   // P only depends on velocities: in-place is safe
-    sT2[s] = T;  // T reads T(y-1) of the input: separate plane
-  }
-  __syncthreads();
-
-  // S2: velocity (velocityShader.frag), needs P(i+1), P(j+1): valid for 1 <= i < SW-1, 1 <= j < SH-1
-  for (int s = tid; s < kN1; s += kNT) {
-    const int j = s / kSW1, i = s - j * kSW1;
-    if (i < kSW1 - 1 && j < kSH1 - 1) {
-      const int wv = sWall[s];
-      float vx = sVX[s], vy = sVY[s];
-      velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + kSW1], (int)(*reinterpret_cast<const char4*>(&wv)).y);
-      sVX[s] = vx;
-      sVY[s] = vy;
-    }
-  }
-  __syncthreads();
-
-  // S3: curl (curlShader.frag): valid for 1 <= i < SW-2, 1 <= j < SH-2
-  for (int s = tid; s < kN1; s += kNT) {
-    const int j = s / kSW1, i = s - j * kSW1;
-    if (i < kSW1 - 2 && j < kSH1 - 2) sCurl[s] = curl_cell(sVX[s], sVY[s], sVX[s + kSW1], sVY[s + 1]);
-  }
-  __syncthreads();
-
-  // S4: vorticity force (vorticityShader.frag): valid for 2 <= i < SW-3, 2 <= j < SH-3
-  for (int s = tid; s < kN1; s += kNT) {
-    const int j = s / kSW1, i = s - j * kSW1;
-    if (i >= 2 && i < kSW1 - 3 && j >= 2 && j < kSH1 - 3) {
-      const float2 vf = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - kSW1], sCurl[s + 1], sCurl[s + kSW1]);
-      sVFX[s] = vf.x;
-      sVFY[s] = vf.y;
-    }
-  }
-  __syncthreads();
-
-  // S5: boundary pass on the TX x TY interior
-  PvbCtx c{sVX, sVY, sP, sT2, sVFX, sVFY, sWall, X0, Y0, glob, fb, dep, useFb};
-  const int tx = tid % kTX, ty0 = tid / kTX;
-#pragma unroll 1
-  for (int ty = ty0; ty < kTY; ty += kNT / kTX) {
-    const int x = X0 + kH1 + tx, y = Y0 + kH1 + ty;
-    if (x < g.cx1 && y < g.H) {
-      float4 b, w;
-      char4 wl;
-      boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
-      const size_t ci = (size_t)y * g.pitch + x;
-      baseOut[ci] = b;
-      waterOut[ci] = w;
-      wallOut[ci] = wl;
-      if (useFb) {  // sprites are sparse: only cells that were hit cost a write
-        const float4 f = fb[ci];
-        if (f.x != 0.0f || f.y != 0.0f || f.z != 0.0f || f.w != 0.0f) fb[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float2 dd = dep[ci];
-        if (dd.x != 0.0f || dd.y != 0.0f) dep[ci] = make_float2(0.f, 0.f);
-      }
+  } else {
+    for (int s = tid; s < N; s += kNT) {
+      const int j = s / SW, i = s - j * SW;
+      const int xx = wrap_x(g, X0 + i);
+      f(s, wrap_y(Y0 + j, g.H) * g.pitch + xx, min(max(Y0 + j, 0), g.H - 1) * g.pitch + xx);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fused_adv
+// Exact slow paths (global memory, any coordinates).  __noinline__ with pointer arguments so that
+// the hot kernels keep their contexts in registers.
 // ---------------------------------------------------------------------------------------------
-constexpr int kH2 = 2;                  // halo: covers every back-trace with |v| < 1
-constexpr int kSW2 = kTX + 2 * kH2;     // 68
-constexpr int kSH2 = kTY + 2 * kH2;     // 20
-constexpr int kN2 = kSW2 * kSH2;        // 1360
-constexpr size_t kSmem2 = (size_t)kN2 * 4 * 9;  // vx vy P T w0 w1 w2 w3 wall
-
-// advection_cell context: tile planes with a bounds check and an exact HBM fallback for
-// back-traces that leave the halo (|v| >= 1 cell / iteration).
-struct AdvCtx {
-  const float *sVX, *sVY, *sP, *sT, *sW0, *sW1, *sW2, *sW3;
-  const int* sWall;
-  int X0, Y0;
-  GlobalCtx glob;  // base_0, water_0, wall_0, light_src
-  __device__ __forceinline__ bool in(int x, int y, int& s) const {
-    const unsigned i = (unsigned)(x - X0), j = (unsigned)(y - Y0);
-    s = (int)(j * kSW2 + i);
-    return i < (unsigned)kSW2 && j < (unsigned)kSH2;
-  }
-  __device__ __forceinline__ int si(int x, int y) const { return (y - Y0) * kSW2 + (x - X0); }
-#define WSB_ADV_ACC(name, plane, fallback) \
-  __device__ __forceinline__ float name(int x, int y) const { int s; return in(x, y, s) ? plane[s] : glob.fallback(x, y); }
-  WSB_ADV_ACC(bx, sVX, bx) WSB_ADV_ACC(by, sVY, by) WSB_ADV_ACC(bp, sP, bp) WSB_ADV_ACC(bt, sT, bt)
-  WSB_ADV_ACC(wt0, sW0, wt0) WSB_ADV_ACC(wt1, sW1, wt1) WSB_ADV_ACC(wt2, sW2, wt2) WSB_ADV_ACC(wt3, sW3, wt3)
-#undef WSB_ADV_ACC
-  __device__ __forceinline__ int wdist(int x, int y) const {
-    int s;
-    if (in(x, y, s)) { int v = sWall[s]; return (int)(*reinterpret_cast<char4*>(&v)).y; }
-    return glob.wdist(x, y);
-  }
-  // fixed +-1 stencil around a cell whose own coordinates are inside the tile or its inner halo
-  __device__ __forceinline__ float sbx(int x, int y) const { return bx(x, y); }
-  __device__ __forceinline__ float sby(int x, int y) const { return by(x, y); }
-  __device__ __forceinline__ float sbt(int x, int y) const { return bt(x, y); }
-  __device__ __forceinline__ int swdist(int x, int y) const { return wdist(x, y); }
-  __device__ __forceinline__ float4 base4(int x, int y) const {
-    int s;
-    if (in(x, y, s)) return make_float4(sVX[s], sVY[s], sP[s], sT[s]);
-    return glob.base4(x, y);
-  }
-  __device__ __forceinline__ float4 water4(int x, int y) const {
-    int s;
-    if (in(x, y, s)) return make_float4(sW0[s], sW1[s], sW2[s], sW3[s]);
-    return glob.water4(x, y);
-  }
-  __device__ __forceinline__ char4 wall4(int x, int y) const {
-    int s;
-    if (in(x, y, s)) { int v = sWall[s]; return *reinterpret_cast<char4*>(&v); }
-    return glob.wall4(x, y);
-  }
-  __device__ __forceinline__ float lightS(int x, int y) const { return glob.lightS(x, y); }
-  __device__ __forceinline__ float lightIRdown(int x, int y) const { return glob.lightIRdown(x, y); }
-  __device__ __forceinline__ float lightIRup(int x, int y) const { return glob.lightIRup(x, y); }
-};
-
-// base_1 temperature of a cell, i.e. the advection result for that cell, computed on demand: the
-// lighting pass needs it for the cell BELOW a water-surface air cell (lightingShader.frag:105).
-__device__ __noinline__ float advected_T(const AdvCtx& c, const Geom& g, const DevParams& d,
-                                         const float* __restrict__ initial_T, const float* __restrict__ sndT,
-                                         const float* __restrict__ sndW, const float* __restrict__ sndV, int x, int y) {
-  float4 b, w;
-  char4 wl;
-  float vm = 0.0f;
-  y = wrap_y(y, g.H);
-  advection_cell<false>(c, g, d, initial_T, sndT, sndW, sndV, x, y, b, w, wl, vm);
-  return b.w;
-}
-
-__global__ void __launch_bounds__(kNT) k_fused_adv(GlobalCtx glob, DevParams d, const float* __restrict__ initial_T,
-                                                   const float* __restrict__ sndT, const float* __restrict__ sndW,
-                                                   const float* __restrict__ sndV, float4* __restrict__ baseOut,
-                                                   float4* __restrict__ waterOut, char4* __restrict__ wallOut,
-                                                   float4* __restrict__ lightOut, unsigned* __restrict__ maxv) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kN2;
-  float* sP = sVY + kN2;
-  float* sT = sP + kN2;
-  float* sW0 = sT + kN2;
-  float* sW1 = sW0 + kN2;
-  float* sW2 = sW1 + kN2;
-  float* sW3 = sW2 + kN2;
-  int* sWall = reinterpret_cast<int*>(sW3 + kN2);
-
-  const Geom& g = glob.g;
-  const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kH2, Y0 = blockIdx.y * kTY - kH2;
-
-  for (int s = tid; s < kN2; s += kNT) {
-    const int j = s / kSW2, i = s - j * kSW2;
-    const size_t ci = (size_t)wrap_y(Y0 + j, g.H) * g.pitch + wrap_x(g, X0 + i);
-    const float4 b = glob.base[ci];
-    const float4 w = glob.water[ci];
-    sVX[s] = b.x; sVY[s] = b.y; sP[s] = b.z; sT[s] = b.w;
-    sW0[s] = w.x; sW1[s] = w.y; sW2[s] = w.z; sW3[s] = w.w;
-    sWall[s] = reinterpret_cast<const int*>(glob.wall)[ci];
-  }
-  __syncthreads();
-
-  AdvCtx c{sVX, sVY, sP, sT, sW0, sW1, sW2, sW3, sWall, X0, Y0, glob};
-  const int tx = tid % kTX, ty0 = tid / kTX;
-  float vm = 0.0f;
-#pragma unroll 1
-  for (int ty = ty0; ty < kTY; ty += kNT / kTX) {
-    const int x = X0 + kH2 + tx, y = Y0 + kH2 + ty;
-    if (x < g.cx1 && y < g.H) {
-      float4 b, w;
-      char4 wl;
-      advection_cell<false>(c, g, d, initial_T, sndT, sndW, sndV, x, y, b, w, wl, vm);
-      const size_t ci = (size_t)y * g.pitch + x;
-      baseOut[ci] = b;
-      waterOut[ci] = w;
-      wallOut[ci] = wl;
-      float TBelow = 0.0f;
-      if (wl.y != 0 && wl.z == 1 && wl.x == WALLTYPE_WATER && (float)y + 0.5f < g.Hf - 1.0f)
-        TBelow = advected_T(c, g, d, initial_T, sndT, sndW, sndV, x, y - 1);
-      lightOut[ci] = lighting_cell(c, g, d, x, y, b.w, w, wl, TBelow);
-    }
-  }
-  report_vmax(vm, maxv);
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_fused_dry — velocity -> advection(base) -> pressure, BASELINE config 2 / the headline sweep
-// ---------------------------------------------------------------------------------------------
-constexpr int kH3 = 3;
-constexpr int kSW3 = kTX + 2 * kH3;  // 70
-constexpr int kSH3 = kTY + 2 * kH3;  // 22
-constexpr int kN3 = kSW3 * kSH3;
-constexpr int kOW3 = kTX + 1, kOH3 = kTY + 1;  // advected region: tile + one column/row on the low side
-constexpr int kNO3 = kOW3 * kOH3;
-constexpr size_t kSmem3 = (size_t)kN3 * 4 * 5 + (size_t)kNO3 * 4 * 4;
-
-// HBM fallback for the dry sweep: applies the velocity pass on the fly to whatever it fetches.
-struct DryGlobalCtx {
-  GlobalCtx glob;  // base_0, wall_0 (pre-velocity)
-  DevParams d;
-  __device__ __forceinline__ float4 post_velocity(int x, int y) const {
+// Raw state = advection output with the pressure pass pending: applies pressure (optionally) and
+// velocity on the fly to whatever it fetches.
+struct RawPvCtx {
+  const GlobalCtx& glob;
+  const DevParams& d;
+  int applyPressure;
+  __device__ float4 post_pressure(int x, int y) const {
     float4 b = glob.base4(x, y);
-    velocity_cell(d, b.x, b.y, b.z, glob.bp(x + 1, y), glob.bp(x, y + 1), glob.wdist(x, y));
+    if (applyPressure) {
+      const char4 wYm = glob.wall4(x, y - 1);
+      pressure_cell(b.x, b.y, b.z, b.w, glob.bx(x - 1, y), glob.by(x, y - 1), glob.bt(x, y - 1), wYm.x, wYm.y);
+    }
     return b;
   }
-};
-
-struct DryCtx {
-  const float *sVX, *sVY, *sP, *sT;
-  const int* sWall;
-  int X0, Y0;
-  DryGlobalCtx dg;
-  __device__ __forceinline__ bool in(int x, int y, int& s) const {
-    // the last staged row / column holds pre-velocity values (velocity needs P(i+1), P(j+1))
-    const unsigned i = (unsigned)(x - X0), j = (unsigned)(y - Y0);
-    s = (int)(j * kSW3 + i);
-    return i < (unsigned)(kSW3 - 1) && j < (unsigned)(kSH3 - 1);
+  __device__ float4 post_pv(int x, int y) const {
+    float4 b = post_pressure(x, y);
+    velocity_cell(d, b.x, b.y, b.z, post_pressure(x + 1, y).z, post_pressure(x, y + 1).z, glob.wdist(x, y));
+    return b;
   }
-#define WSB_DRY_ACC(name, plane, comp) \
-  __device__ __forceinline__ float name(int x, int y) const { int s; return in(x, y, s) ? plane[s] : dg.post_velocity(x, y).comp; }
-  WSB_DRY_ACC(bx, sVX, x) WSB_DRY_ACC(by, sVY, y) WSB_DRY_ACC(bp, sP, z) WSB_DRY_ACC(bt, sT, w)
-#undef WSB_DRY_ACC
+  __device__ __forceinline__ float bx(int x, int y) const { return post_pv(x, y).x; }
+  __device__ __forceinline__ float by(int x, int y) const { return post_pv(x, y).y; }
+  __device__ __forceinline__ float bp(int x, int y) const { return post_pv(x, y).z; }
+  __device__ __forceinline__ float bt(int x, int y) const { return post_pv(x, y).w; }
   __device__ __forceinline__ float sbx(int x, int y) const { return bx(x, y); }
   __device__ __forceinline__ float sby(int x, int y) const { return by(x, y); }
   __device__ __forceinline__ float sbt(int x, int y) const { return bt(x, y); }
-  __device__ __forceinline__ int wdist(int x, int y) const {
-    int s;
-    const unsigned i = (unsigned)(x - X0), j = (unsigned)(y - Y0);
-    s = (int)(j * kSW3 + i);
-    if (i < (unsigned)kSW3 && j < (unsigned)kSH3) { int v = sWall[s]; return (int)(*reinterpret_cast<char4*>(&v)).y; }
-    return dg.glob.wdist(x, y);
-  }
-  __device__ __forceinline__ int swdist(int x, int y) const { return wdist(x, y); }
-  __device__ __forceinline__ float4 base4(int x, int y) const {
-    int s;
-    if (in(x, y, s)) return make_float4(sVX[s], sVY[s], sP[s], sT[s]);
-    return dg.post_velocity(x, y);
-  }
-  __device__ __forceinline__ char4 wall4(int x, int y) const {
-    int s;
-    const unsigned i = (unsigned)(x - X0), j = (unsigned)(y - Y0);
-    s = (int)(j * kSW3 + i);
-    if (i < (unsigned)kSW3 && j < (unsigned)kSH3) { int v = sWall[s]; return *reinterpret_cast<char4*>(&v); }
-    return dg.glob.wall4(x, y);
-  }
+  __device__ __forceinline__ float4 base4(int x, int y) const { return post_pv(x, y); }
+  __device__ __forceinline__ char4 wall4(int x, int y) const { return glob.wall4(x, y); }
+  __device__ __forceinline__ int wdist(int x, int y) const { return glob.wdist(x, y); }
+  __device__ __forceinline__ int swdist(int x, int y) const { return glob.wdist(x, y); }
   // the dry sweep does not touch water
   __device__ __forceinline__ float4 water4(int, int) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
   __device__ __forceinline__ float wt0(int, int) const { return 0.f; }
@@ -360,75 +123,455 @@ struct DryCtx {
   __device__ __forceinline__ float wt3(int, int) const { return 0.f; }
 };
 
-__global__ void __launch_bounds__(kNT) k_fused_dry(GlobalCtx glob, DevParams d, float4* __restrict__ baseOut,
-                                                   unsigned* __restrict__ maxv) {
+__device__ __noinline__ float4 dry_advect_slow(const GlobalCtx* glob, const DevParams* d, int applyPressure, int x, int y,
+                                               float* vm) {
+  RawPvCtx c{*glob, *d, applyPressure};
+  float4 b, w;
+  char4 wl;
+  advection_cell<true>(c, glob->g, *d, nullptr, nullptr, nullptr, nullptr, x, y, b, w, wl, *vm);
+  return b;
+}
+
+struct AdvSlowOut { float4 base, water; char4 wall; float vm; };
+__device__ __noinline__ void adv_cell_slow(const GlobalCtx* glob, const DevParams* d, const float* initial_T, const float* sndT,
+                                           const float* sndW, const float* sndV, int x, int y, AdvSlowOut* out) {
+  out->vm = 0.0f;
+  advection_cell<false>(*glob, glob->g, *d, initial_T, sndT, sndW, sndV, x, y, out->base, out->water, out->wall, out->vm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory gathers of the semi-Lagrangian back-trace
+// ---------------------------------------------------------------------------------------------
+// Tile-local index of a bilerp's lower-left texel; `lxBase` = tile-local column of the cell whose
+// fragCoord started the trace, gx its global column, Y0 the global row of tile row 0.
+template <int SW>
+__device__ __forceinline__ int tile_index(const BilerpSetup& b, int lxBase, int gx, int Y0, int& lx, int& ly) {
+  lx = lxBase + (b.ix - gx);
+  ly = b.iy - Y0;
+  return ly * SW + lx;
+}
+// all four texels (lx..lx+1, ly..ly+1) inside [lo, SW-1-hi] x [lo, SH-1-hi]
+template <int SW, int SH>
+__device__ __forceinline__ bool tile_ok(int lx, int ly, int lo, int hi) {
+  return (unsigned)(lx - lo) <= (unsigned)(SW - 2 - hi - lo) && (unsigned)(ly - lo) <= (unsigned)(SH - 2 - hi - lo);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_dry — pressure(prev) -> velocity -> advection(base): BASELINE config 2 / headline sweep
+// ---------------------------------------------------------------------------------------------
+constexpr int kHD = 2;                   // raw halo: advection +-1 of post-velocity, velocity +1, pressure -1
+constexpr int kSWD = kTX + 2 * kHD;      // 68
+constexpr int kSHD = kTY + 2 * kHD;      // 20
+constexpr int kND = kSWD * kSHD;         // 1360
+constexpr size_t kSmemDry = (size_t)kND * (8 + 8 + 8 + 4);  // V, PT raw, PT post-pressure, wall
+
+// glob: base = base_1 (advection output, pressure pending), wall = wall_1.
+__global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ GlobalCtx glob,
+                                                      const __grid_constant__ DevParams d, int applyPressure,
+                                                      float4* __restrict__ baseOut, unsigned* __restrict__ maxv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kN3;
-  float* sP = sVY + kN3;
-  float* sT = sP + kN3;
-  int* sWall = reinterpret_cast<int*>(sT + kN3);
-  float* oVX = reinterpret_cast<float*>(sWall + kN3);
-  float* oVY = oVX + kNO3;
-  float* oP = oVY + kNO3;
-  float* oT = oP + kNO3;
+  float2* sV = reinterpret_cast<float2*>(smem_raw);
+  float2* sPT = sV + kND;
+  float2* sPT2 = sPT + kND;
+  int* sWl = reinterpret_cast<int*>(sPT2 + kND);
+  constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kH3, Y0 = blockIdx.y * kTY - kH3;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kHD, Y0 = blockIdx.y * kTY - kHD;
 
-  for (int s = tid; s < kN3; s += kNT) {
-    const int j = s / kSW3, i = s - j * kSW3;
-    const size_t ci = (size_t)wrap_y(Y0 + j, g.H) * g.pitch + wrap_x(g, X0 + i);
-    const float4 b = glob.base[ci];
-    sVX[s] = b.x; sVY[s] = b.y; sP[s] = b.z; sT[s] = b.w;
-    sWall[s] = reinterpret_cast<const int*>(glob.wall)[ci];
+  for_each_staged<kSWD, kSHD>(g, X0, Y0, [&](int s, int ci, int) {
+    const float* src = reinterpret_cast<const float*>(glob.base + ci);
+    cp_async8(&sV[s], src);
+    cp_async8(&sPT[s], src + 2);
+    cp_async4(&sWl[s], glob.wall + ci);
+  });
+  cp_async_wait_all();
+  __syncthreads();
+
+  // pressure pass of the previous iteration (pressureShader.frag); valid for i >= 1, j >= 1
+  for (int s = SW + tid; s < kND; s += kNT) {
+    const float2 v = sV[s];
+    float2 pt = sPT[s];
+    if (applyPressure) {
+      const char4 wYm = as_char4(sWl[s - SW]);
+      pressure_cell(v.x, v.y, pt.x, pt.y, sV[s - 1].x, sV[s - SW].y, sPT[s - SW].y, wYm.x, wYm.y);
+    }
+    sPT2[s] = pt;
+  }
+  __syncthreads();
+  // velocity (velocityShader.frag), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
+  for (int s = SW + tid; s < kND - SW; s += kNT) {
+    float2 v = sV[s];
+    velocity_cell(d, v.x, v.y, sPT2[s].x, sPT2[s + 1].x, sPT2[s + SW].x, (int)as_char4(sWl[s]).y);
+    sV[s] = v;
   }
   __syncthreads();
 
-  // velocity in place (only the cell's own velocity changes); last row / column stay pre-velocity
-  for (int s = tid; s < kN3; s += kNT) {
-    const int j = s / kSW3, i = s - j * kSW3;
-    if (i < kSW3 - 1 && j < kSH3 - 1) {
-      const int wv = sWall[s];
-      float vx = sVX[s], vy = sVY[s];
-      velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + kSW3], (int)(*reinterpret_cast<const char4*>(&wv)).y);
-      sVX[s] = vx;
-      sVY[s] = vy;
+  // advection of the base field on the tile
+  const int tx = tid % kTX, ty0 = tid / kTX;
+  const int x = X0 + kHD + tx;
+  float vm = 0.0f;
+  if (x < g.cx1) {
+    const int gx = global_x(g, x);
+    const float fragCoordX = (float)gx + 0.5f;
+    const int lxBase = tx + kHD;
+#pragma unroll 1
+    for (int ty = ty0; ty < kTY; ty += kRowStep) {
+      const int y = Y0 + kHD + ty;
+      if (y >= g.H) break;
+      const int c = (ty + kHD) * SW + lxBase;
+      const float fragCoordY = (float)y + 0.5f;
+      const char4 w0 = as_char4(sWl[c]);
+      float4 base;
+      if (w0.y != 0) {
+        const float2 v00 = sV[c];
+        vm = fmaxf(vm, fmaxf(fabsf(v00.x), fabsf(v00.y)));
+        const AdvVel a = adv_velocities(v00.x, v00.y, sV[c - 1].x, sV[c - SW].y, sV[c + 1].y, sV[c + SW].x, sV[c + SW - 1].x,
+                                        sV[c - SW + 1].y);
+        const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
+        const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
+        const BilerpSetup b3 = bilerp_setup(fragCoordX - a.Px, fragCoordY - a.Py);
+        int lx1, ly1, lx2, ly2, lx3, ly3;
+        const int l1 = tile_index<SW>(b1, lxBase, gx, Y0, lx1, ly1);
+        const int l2 = tile_index<SW>(b2, lxBase, gx, Y0, lx2, ly2);
+        const int l3 = tile_index<SW>(b3, lxBase, gx, Y0, lx3, ly3);
+        // post-velocity / post-pressure planes are valid on [1, SW-2] x [1, SH-2]
+        if (tile_ok<kSWD, kSHD>(lx1, ly1, 1, 1) && tile_ok<kSWD, kSHD>(lx2, ly2, 1, 1) && tile_ok<kSWD, kSHD>(lx3, ly3, 1, 1)) {
+          base.x = mix2d(sV[l1].x, sV[l1 + 1].x, sV[l1 + SW].x, sV[l1 + SW + 1].x, b1.fx, b1.fx, b1.fy);
+          base.y = mix2d(sV[l2].y, sV[l2 + 1].y, sV[l2 + SW].y, sV[l2 + SW + 1].y, b2.fx, b2.fx, b2.fy);
+          const WallMix m = wall_mix(as_char4(sWl[l3]).y, as_char4(sWl[l3 + 1]).y, as_char4(sWl[l3 + SW]).y,
+                                     as_char4(sWl[l3 + SW + 1]).y, b3.fx, b3.fy);
+          const float2 pa = sPT2[l3], pb = sPT2[l3 + 1], pc = sPT2[l3 + SW], pd = sPT2[l3 + SW + 1];
+          base.z = mix2d(pa.x, pb.x, pc.x, pd.x, m.ab, m.cd, m.abcd);
+          base.w = mix2d(pa.y, pb.y, pc.y, pd.y, m.ab, m.cd, m.abcd);
+        } else {
+          float vmSlow = 0.0f;  // a local of the cold branch: keeps vm itself in a register
+          base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
+          vm = fmaxf(vm, vmSlow);
+        }
+      } else {  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
+        const float2 v = sV[c], pt = sPT2[c];
+        base = make_float4(v.x, v.y, pt.x, (w0.x == WALLTYPE_LAND) ? 1000.0f : pt.y);
+      }
+      baseOut[(size_t)y * g.pitch + x] = base;
     }
   }
+  report_vmax(vm, maxv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_pvb — pressure(prev) -> velocity -> curl -> vorticity -> boundary
+// ---------------------------------------------------------------------------------------------
+constexpr int kH1 = 3;                      // halo of the pressure->boundary chain
+constexpr int kSW1 = kTX + 2 * kH1;         // 70
+constexpr int kSH1 = kTY + 2 * kH1;         // 22
+constexpr int kN1 = kSW1 * kSH1;            // 1540 cells per staged tile
+// V (8) | PT raw, later curl (8) | PT post-pressure (8) | wall (4) | vortForce (8)
+constexpr size_t kSmem1 = (size_t)kN1 * (8 + 8 + 8 + 4 + 8);
+
+// boundary_cell context positioned at shared-memory cell c: base / wall / vortForce from the tile,
+// own-cell water / light / feedback / deposition from registers (prefetched), the sparse
+// neighbour fetches of water and light (surface cells only) from HBM.
+struct PvbAt {
+  const float2 *sV, *sPT2, *sVF;
+  const int* sWl;
+  int c;
+  const GlobalCtx& glob;
+  int x, y;
+  float4 water0, fb0;
+  float2 light0, dep0;
+  __device__ __forceinline__ int si(int dx, int dy) const { return c + dy * kSW1 + dx; }
+  __device__ __forceinline__ float4 base4(int dx, int dy) const {
+    const float2 v = sV[si(dx, dy)], pt = sPT2[si(dx, dy)];
+    return make_float4(v.x, v.y, pt.x, pt.y);
+  }
+  __device__ __forceinline__ float bx(int dx, int dy) const { return sV[si(dx, dy)].x; }
+  __device__ __forceinline__ float by(int dx, int dy) const { return sV[si(dx, dy)].y; }
+  __device__ __forceinline__ float bt(int dx, int dy) const { return sPT2[si(dx, dy)].y; }
+  __device__ __forceinline__ char4 wall4(int dx, int dy) const { return as_char4(sWl[si(dx, dy)]); }
+  __device__ __forceinline__ float2 vort(int dx, int dy) const { return sVF[si(dx, dy)]; }
+  __device__ __forceinline__ float4 water4(int dx, int dy) const {
+    if (dx == 0 && dy == 0) return water0;
+    return glob.water[glob.idx_near(x + dx, y + dy)];
+  }
+  __device__ __forceinline__ float4 light4(int dx, int dy) const {
+    if (dx == 0 && dy == 0) return make_float4(light0.x, light0.y, 0.0f, 0.0f);  // boundary reads SUNLIGHT, NET_HEATING only
+    return glob.light4(x + dx, y + dy);
+  }
+  __device__ __forceinline__ float4 fb4() const { return fb0; }
+  __device__ __forceinline__ float2 dep2() const { return dep0; }
+};
+
+// glob: base = base_1, wall = wall_1, water = water_1, light = light_0 (glob.fb / glob.dep unused).
+// useFb: feedback / deposition hold data from the last particle pass; the kernel consumes them and
+// writes the zeros of the reference's gl.clear (app.js:5933-5934) back to the cells that were hit.
+__global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
+                                                      const __grid_constant__ DevParams d,
+                                                      const float* __restrict__ initial_T, int applyPressure, int useFb,
+                                                      float4* fb, float2* dep, float4* __restrict__ baseOut,
+                                                      float4* __restrict__ waterOut, char4* __restrict__ wallOut) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sV = reinterpret_cast<float2*>(smem_raw);
+  float2* sPT = sV + kN1;                           // raw (P, T); dead after the pressure sweep
+  float* sCurl = reinterpret_cast<float*>(sPT);     // ... then curl
+  float2* sPT2 = sPT + kN1;                         // post-pressure (P, T)
+  int* sWl = reinterpret_cast<int*>(sPT2 + kN1);
+  float2* sVF = reinterpret_cast<float2*>(sWl + kN1);
+  constexpr int SW = kSW1;
+
+  const Geom& g = glob.g;
+  const int tid = threadIdx.x;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kH1, Y0 = blockIdx.y * kTY - kH1;
+
+  for_each_staged<kSW1, kSH1>(g, X0, Y0, [&](int s, int ci, int) {
+    const float* src = reinterpret_cast<const float*>(glob.base + ci);
+    cp_async8(&sV[s], src);
+    cp_async8(&sPT[s], src + 2);
+    cp_async4(&sWl[s], glob.wall + ci);
+  });
+
+  // own-cell operands of the boundary pass: first row now (in flight during the sweeps below),
+  // the following rows one step ahead of their use
+  const int tx = tid % kTX, ty0 = tid / kTX;
+  const int x = X0 + kH1 + tx;
+  const bool colOk = x < g.cx1;
+  float4 waterN = make_float4(0.f, 0.f, 0.f, 0.f), fbN = waterN;
+  float2 lightN = make_float2(0.f, 0.f), depN = lightN;
+  auto prefetch = [&](int ty) {
+    const int y = Y0 + kH1 + ty;
+    if (colOk && ty < kTY && y < g.H) {
+      const int ci = y * g.pitch + x;
+      waterN = glob.water[ci];
+      lightN = *reinterpret_cast<const float2*>(glob.light + ci);
+      if (useFb) {
+        fbN = fb[ci];
+        depN = dep[ci];
+      }
+    }
+  };
+  prefetch(ty0);
+
+  cp_async_wait_all();
   __syncthreads();
 
-  // advection of the base field on the tile plus one column / row on the low side
-  DryCtx c{sVX, sVY, sP, sT, sWall, X0, Y0, DryGlobalCtx{glob, d}};
-  float vm = 0.0f;
-  for (int o = tid; o < kNO3; o += kNT) {
-    const int oj = o / kOW3, oi = o - oj * kOW3;
-    const int x = X0 + kH3 - 1 + oi, y = Y0 + kH3 - 1 + oj;  // unwrapped cell coordinates
-    float4 b, w;
-    char4 wl;
-    // coordinates used for fragCoord must be the wrapped ones
-    const int xw = g.wrap ? (x < 0 ? x + g.pitch : (x >= g.pitch ? x - g.pitch : x)) : x;
-    const int yw = wrap_y(y, g.H);
-    DryCtx cw = c;
-    cw.X0 = X0 + (xw - x);
-    cw.Y0 = Y0 + (yw - y);
-    advection_cell<true>(cw, g, d, nullptr, nullptr, nullptr, nullptr, xw, yw, b, w, wl, vm);
-    oVX[o] = b.x; oVY[o] = b.y; oP[o] = b.z; oT[o] = b.w;
+  // S1: pressure pass of the previous iteration; valid for i >= 1, j >= 1
+  for (int s = SW + tid; s < kN1; s += kNT) {
+    const float2 v = sV[s];
+    float2 pt = sPT[s];
+    if (applyPressure) {
+      const char4 wYm = as_char4(sWl[s - SW]);
+      pressure_cell(v.x, v.y, pt.x, pt.y, sV[s - 1].x, sV[s - SW].y, sPT[s - SW].y, wYm.x, wYm.y);
+    }
+    sPT2[s] = pt;
   }
   __syncthreads();
+  // S2: velocity in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
+  for (int s = SW + tid; s < kN1 - SW; s += kNT) {
+    float2 v = sV[s];
+    velocity_cell(d, v.x, v.y, sPT2[s].x, sPT2[s + 1].x, sPT2[s + SW].x, (int)as_char4(sWl[s]).y);
+    sV[s] = v;
+  }
+  __syncthreads();
+  // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw PT plane is dead: reuse it)
+  for (int s = SW + tid; s < kN1 - 2 * SW; s += kNT) {
+    const float2 v = sV[s];
+    sCurl[s] = curl_cell(v.x, v.y, sV[s + SW].x, sV[s + 1].y);
+  }
+  __syncthreads();
+  // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
+  // valid for 2 <= i <= SW-4
+  for (int s = (kH1 - 1) * SW + tid; s < (kH1 + kTY) * SW; s += kNT)
+    sVF[s] = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - SW], sCurl[s + 1], sCurl[s + SW]);
+  __syncthreads();
 
-  // pressure on the tile
+  // S5: boundary pass on the TX x TY interior
+#pragma unroll 1
+  for (int ty = ty0; ty < kTY; ty += kRowStep) {
+    const int y = Y0 + kH1 + ty;
+    PvbAt c{sV, sPT2, sVF, sWl, (ty + kH1) * SW + tx + kH1, glob, x, y, waterN, fbN, lightN, depN};
+    prefetch(ty + kRowStep);
+    if (colOk && y < g.H) {
+      float4 b, w;
+      char4 wl;
+      boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
+      const size_t ci = (size_t)y * g.pitch + x;
+      baseOut[ci] = b;
+      waterOut[ci] = w;
+      wallOut[ci] = wl;
+      if (useFb) {  // sprites are sparse: only cells that were hit cost a write
+        if (c.fb0.x != 0.0f || c.fb0.y != 0.0f || c.fb0.z != 0.0f || c.fb0.w != 0.0f) fb[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.dep0.x != 0.0f || c.dep0.y != 0.0f) dep[ci] = make_float2(0.f, 0.f);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fused_adv — advection -> lighting
+// ---------------------------------------------------------------------------------------------
+constexpr int kH2 = 2;                  // halo: covers every back-trace with |v| < 1 and the sun-ray fetch
+constexpr int kSW2 = kTX + 2 * kH2;     // 68
+constexpr int kSH2 = kTY + 2 * kH2;     // 20
+constexpr int kN2 = kSW2 * kSH2;        // 1360
+// V 8 | PT 8 | water(total, cloud) 8 | precip 4 | smoke 4 | wall 4 | light: sun 4, IR down 4, IR up 4
+constexpr size_t kSmem2 = (size_t)kN2 * (8 + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4);
+
+// light fetches of lighting_cell from the staged light planes (rows are staged with the
+// CLAMP_TO_EDGE rule, so the clamped row lighting_cell passes maps straight to a tile row)
+struct TileLightCtx {
+  const float *sLS, *sLD, *sLU;
+  int X0, Y0;
+  __device__ __forceinline__ int si(int x, int y) const { return (y - Y0) * kSW2 + (x - X0); }
+  __device__ __forceinline__ float lightS(int x, int y) const { return sLS[si(x, y)]; }
+  __device__ __forceinline__ float lightIRdown(int x, int y) const { return sLD[si(x, y)]; }
+  __device__ __forceinline__ float lightIRup(int x, int y) const { return sLU[si(x, y)]; }
+};
+
+// glob: base_0, water_0, wall_0 (boundary output), light = light_src.
+__global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ GlobalCtx glob,
+                                                      const __grid_constant__ DevParams d,
+                                                      const float* __restrict__ initial_T, const float* __restrict__ sndT,
+                                                      const float* __restrict__ sndW, const float* __restrict__ sndV,
+                                                      float4* __restrict__ baseOut, float4* __restrict__ waterOut,
+                                                      char4* __restrict__ wallOut, float4* __restrict__ lightOut,
+                                                      unsigned* __restrict__ maxv) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sV = reinterpret_cast<float2*>(smem_raw);
+  float2* sPT = sV + kN2;
+  float2* sW01 = sPT + kN2;
+  float* sW2 = reinterpret_cast<float*>(sW01 + kN2);
+  float* sW3 = sW2 + kN2;
+  int* sWl = reinterpret_cast<int*>(sW3 + kN2);
+  float* sLS = reinterpret_cast<float*>(sWl + kN2);
+  float* sLD = sLS + kN2;
+  float* sLU = sLD + kN2;
+  constexpr int SW = kSW2;
+
+  const Geom& g = glob.g;
+  const int tid = threadIdx.x;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kH2, Y0 = blockIdx.y * kTY - kH2;
+
+  for_each_staged<kSW2, kSH2>(g, X0, Y0, [&](int s, int ci, int cil) {
+    const float* bsrc = reinterpret_cast<const float*>(glob.base + ci);
+    const float* wsrc = reinterpret_cast<const float*>(glob.water + ci);
+    const float* lsrc = reinterpret_cast<const float*>(glob.light + cil);
+    cp_async8(&sV[s], bsrc);
+    cp_async8(&sPT[s], bsrc + 2);
+    cp_async8(&sW01[s], wsrc);
+    cp_async4(&sW2[s], wsrc + 2);
+    cp_async4(&sW3[s], wsrc + 3);
+    cp_async4(&sWl[s], glob.wall + ci);
+    cp_async4(&sLS[s], lsrc);
+    cp_async4(&sLD[s], lsrc + 2);
+    cp_async4(&sLU[s], lsrc + 3);
+  });
+  cp_async_wait_all();
+  __syncthreads();
+
+  const TileLightCtx lc{sLS, sLD, sLU, X0, Y0};
   const int tx = tid % kTX, ty0 = tid / kTX;
-  for (int ty = ty0; ty < kTY; ty += kNT / kTX) {
-    const int x = X0 + kH3 + tx, y = Y0 + kH3 + ty;
-    if (x < g.cx1 && y < g.H) {
-      const int o = (ty + 1) * kOW3 + (tx + 1);
-      const int wv = sWall[(ty + kH3 - 1) * kSW3 + (tx + kH3)];
-      const char4 wYm = *reinterpret_cast<const char4*>(&wv);
-      float4 b = make_float4(oVX[o], oVY[o], oP[o], oT[o]);
-      pressure_cell(b.x, b.y, b.z, b.w, oVX[o - 1], oVY[o - kOW3], oT[o - kOW3], wYm.x, wYm.y);
-      baseOut[(size_t)y * g.pitch + x] = b;
+  const int x = X0 + kH2 + tx;
+  float vm = 0.0f;
+  if (x < g.cx1) {
+    const int gx = global_x(g, x);
+    const float fragCoordX = (float)gx + 0.5f;
+    const float texCoordX = fragCoordX * g.texelX;
+    const int lxBase = tx + kH2;
+#pragma unroll 1
+    for (int ty = ty0; ty < kTY; ty += kRowStep) {
+      const int y = Y0 + kH2 + ty;
+      if (y >= g.H) break;
+      const int c = (ty + kH2) * SW + lxBase;
+      const float fragCoordY = (float)y + 0.5f;
+      const float texCoordY = fragCoordY * g.texelY;
+      const char4 w0 = as_char4(sWl[c]);
+      int wType = w0.x, wDist = w0.y, wVert = w0.z, wVeg = w0.w;
+      const int aboveDist = as_char4(sWl[c + SW]).y;
+      float4 base, water;
+      char4 wl;
+      bool done = false;
+      if (wDist != 0) {  // air: semi-Lagrangian gathers from the tile
+        const float2 v00 = sV[c];
+        const AdvVel a = adv_velocities(v00.x, v00.y, sV[c - 1].x, sV[c - SW].y, sV[c + 1].y, sV[c + SW].x, sV[c + SW - 1].x,
+                                        sV[c - SW + 1].y);
+        const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
+        const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
+        const float posPx = fragCoordX - a.Px, posPy = fragCoordY - a.Py;
+        const BilerpSetup b3 = bilerp_setup(posPx, posPy);
+        const BilerpSetup b4 = bilerp_setup(posPx + 0.0f, posPy + 0.05f);
+        int lx1, ly1, lx2, ly2, lx3, ly3, lx4, ly4;
+        const int l1 = tile_index<SW>(b1, lxBase, gx, Y0, lx1, ly1);
+        const int l2 = tile_index<SW>(b2, lxBase, gx, Y0, lx2, ly2);
+        const int l3 = tile_index<SW>(b3, lxBase, gx, Y0, lx3, ly3);
+        const int l4 = tile_index<SW>(b4, lxBase, gx, Y0, lx4, ly4);
+        if (tile_ok<kSW2, kSH2>(lx1, ly1, 0, 0) && tile_ok<kSW2, kSH2>(lx2, ly2, 0, 0) && tile_ok<kSW2, kSH2>(lx3, ly3, 0, 0) &&
+            tile_ok<kSW2, kSH2>(lx4, ly4, 0, 0)) {
+          vm = fmaxf(vm, fmaxf(fabsf(v00.x), fabsf(v00.y)));
+          base.x = mix2d(sV[l1].x, sV[l1 + 1].x, sV[l1 + SW].x, sV[l1 + SW + 1].x, b1.fx, b1.fx, b1.fy);
+          base.y = mix2d(sV[l2].y, sV[l2 + 1].y, sV[l2 + SW].y, sV[l2 + SW + 1].y, b2.fx, b2.fx, b2.fy);
+          {
+            const WallMix m = wall_mix(as_char4(sWl[l3]).y, as_char4(sWl[l3 + 1]).y, as_char4(sWl[l3 + SW]).y,
+                                       as_char4(sWl[l3 + SW + 1]).y, b3.fx, b3.fy);
+            const float2 pa = sPT[l3], pb = sPT[l3 + 1], pc = sPT[l3 + SW], pd = sPT[l3 + SW + 1];
+            base.z = mix2d(pa.x, pb.x, pc.x, pd.x, m.ab, m.cd, m.abcd);
+            base.w = mix2d(pa.y, pb.y, pc.y, pd.y, m.ab, m.cd, m.abcd);
+            const float2 qa = sW01[l3], qb = sW01[l3 + 1], qc = sW01[l3 + SW], qd = sW01[l3 + SW + 1];
+            water.x = mix2d(qa.x, qb.x, qc.x, qd.x, m.ab, m.cd, m.abcd);
+            water.y = mix2d(qa.y, qb.y, qc.y, qd.y, m.ab, m.cd, m.abcd);
+            water.w = mix2d(sW3[l3], sW3[l3 + 1], sW3[l3 + SW], sW3[l3 + SW + 1], m.ab, m.cd, m.abcd);
+          }
+          {
+            const WallMix m = wall_mix(as_char4(sWl[l4]).y, as_char4(sWl[l4 + 1]).y, as_char4(sWl[l4 + SW]).y,
+                                       as_char4(sWl[l4 + SW + 1]).y, b4.fx, b4.fy);
+            water.z = mix2d(sW2[l4], sW2[l4 + 1], sW2[l4 + SW], sW2[l4 + SW + 1], m.ab, m.cd, m.abcd);
+          }
+          adv_air_thermo(g, d, sndT, sndW, sndV, texCoordY, base, water);
+        } else {  // a back-trace left the halo: exact global-memory path for the whole cell
+          AdvSlowOut o;
+          adv_cell_slow(&glob, &d, initial_T, sndT, sndW, sndV, x, y, &o);
+          base = o.base;
+          water = o.water;
+          wl = o.wall;
+          vm = fmaxf(vm, o.vm);
+          done = true;
+        }
+      } else {  // wall: pass-through + surface processes
+        const float2 v = sV[c], pt = sPT[c], w01 = sW01[c];
+        base = make_float4(v.x, v.y, pt.x, pt.y);
+        water = make_float4(w01.x, w01.y, sW2[c], sW3[c]);
+        adv_wall_cell<false>(d, texCoordY, wType, aboveDist, sPT[c + SW].y, wVeg, base, water);
+      }
+      if (!done) {
+        adv_user_input(g, d, initial_T, texCoordX, texCoordY, aboveDist, wType, wDist, wVert, wVeg, base, water);
+        wl = pack_wall(wType, wDist, wVert, wVeg);
+      }
+      const size_t ci = (size_t)y * g.pitch + x;
+      baseOut[ci] = base;
+      waterOut[ci] = water;
+      wallOut[ci] = wl;
+
+      // lighting needs base_1's temperature of the cell BELOW a water-surface air cell
+      // (lightingShader.frag:105), i.e. that cell's advection result
+      float TBelow = 0.0f;
+      if (wl.y != 0 && wl.z == 1 && wl.x == WALLTYPE_WATER && fragCoordY < g.Hf - 1.0f) {
+        const int cb = c - SW;
+        const char4 wb = as_char4(sWl[cb]);
+        if (wb.y == 0) {  // the usual case: a wall cell, whose advection is a local update
+          int tB = wb.x, dB = wb.y, vB = wb.w;
+          const float2 vb = sV[cb], ptb = sPT[cb], w01b = sW01[cb];
+          float4 bb = make_float4(vb.x, vb.y, ptb.x, ptb.y), wtb = make_float4(w01b.x, w01b.y, sW2[cb], sW3[cb]);
+          const float texCoordYb = ((float)wrap_y(y - 1, g.H) + 0.5f) * g.texelY;
+          adv_wall_cell<false>(d, texCoordYb, tB, w0.y, sPT[c].y, vB, bb, wtb);
+          adv_user_input(g, d, initial_T, texCoordX, texCoordYb, w0.y, tB, dB, wb.z, vB, bb, wtb);
+          TBelow = bb.w;
+        } else {
+          AdvSlowOut o;
+          adv_cell_slow(&glob, &d, initial_T, sndT, sndW, sndV, x, wrap_y(y - 1, g.H), &o);
+          TBelow = o.base.w;
+        }
+      }
+      lightOut[ci] = lighting_cell(lc, g, d, x, y, base.w, water, wl, TBelow);
     }
   }
   report_vmax(vm, maxv);

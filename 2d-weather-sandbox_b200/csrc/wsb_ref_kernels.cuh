@@ -19,6 +19,8 @@ struct GlobalCtx {
   Geom g;
   // any (x, y): periodic in y, periodic (single domain) or clamped (strip) in x
   __device__ __forceinline__ size_t idx(int x, int y) const { return (size_t)mod_i(y, g.H) * g.pitch + gather_x(g, x); }
+  // (x, y) at most one period outside the array (fixed +-1 stencils): no integer division
+  __device__ __forceinline__ size_t idx_near(int x, int y) const { return (size_t)wrap_y(y, g.H) * g.pitch + wrap_x(g, x); }
   __device__ __forceinline__ float4 base4(int x, int y) const { return base[idx(x, y)]; }
   __device__ __forceinline__ float bx(int x, int y) const { return reinterpret_cast<const float*>(base)[idx(x, y) * 4 + 0]; }
   __device__ __forceinline__ float by(int x, int y) const { return reinterpret_cast<const float*>(base)[idx(x, y) * 4 + 1]; }
@@ -37,13 +39,29 @@ struct GlobalCtx {
   __device__ __forceinline__ int wdist(int x, int y) const { return reinterpret_cast<const signed char*>(wall)[idx(x, y) * 4 + 1]; }
   __device__ __forceinline__ float2 vort(int x, int y) const { return vortf[idx(x, y)]; }
   // light texture: wrap S = REPEAT, wrap T = CLAMP_TO_EDGE (app.js:5276-5279)
-  __device__ __forceinline__ size_t lidx(int x, int y) const { return (size_t)min(max(y, 0), g.H - 1) * g.pitch + gather_x(g, x); }
+  __device__ __forceinline__ size_t lidx(int x, int y) const { return (size_t)min(max(y, 0), g.H - 1) * g.pitch + wrap_x(g, x); }
   __device__ __forceinline__ float4 light4(int x, int y) const { return light[lidx(x, y)]; }
   __device__ __forceinline__ float lightS(int x, int y) const { return reinterpret_cast<const float*>(light)[lidx(x, y) * 4 + 0]; }
   __device__ __forceinline__ float lightIRdown(int x, int y) const { return reinterpret_cast<const float*>(light)[lidx(x, y) * 4 + 2]; }
   __device__ __forceinline__ float lightIRup(int x, int y) const { return reinterpret_cast<const float*>(light)[lidx(x, y) * 4 + 3]; }
   __device__ __forceinline__ float4 fb4(int x, int y) const { return fb[idx(x, y)]; }
   __device__ __forceinline__ float2 dep2(int x, int y) const { return dep[idx(x, y)]; }
+};
+
+// GlobalCtx positioned at a cell: the offset-style fetches boundary_cell asks for.
+struct GlobalAt {
+  const GlobalCtx& c;
+  int x, y;
+  __device__ __forceinline__ float4 base4(int dx, int dy) const { return c.base[c.idx_near(x + dx, y + dy)]; }
+  __device__ __forceinline__ float bx(int dx, int dy) const { return reinterpret_cast<const float*>(c.base)[c.idx_near(x + dx, y + dy) * 4 + 0]; }
+  __device__ __forceinline__ float by(int dx, int dy) const { return reinterpret_cast<const float*>(c.base)[c.idx_near(x + dx, y + dy) * 4 + 1]; }
+  __device__ __forceinline__ float bt(int dx, int dy) const { return reinterpret_cast<const float*>(c.base)[c.idx_near(x + dx, y + dy) * 4 + 3]; }
+  __device__ __forceinline__ float4 water4(int dx, int dy) const { return c.water[c.idx_near(x + dx, y + dy)]; }
+  __device__ __forceinline__ char4 wall4(int dx, int dy) const { return c.wall[c.idx_near(x + dx, y + dy)]; }
+  __device__ __forceinline__ float2 vort(int dx, int dy) const { return c.vortf[c.idx_near(x + dx, y + dy)]; }
+  __device__ __forceinline__ float4 light4(int dx, int dy) const { return c.light4(x + dx, y + dy); }
+  __device__ __forceinline__ float4 fb4() const { return c.fb[(size_t)y * c.g.pitch + x]; }
+  __device__ __forceinline__ float2 dep2() const { return c.dep[(size_t)y * c.g.pitch + x]; }
 };
 
 #define WSB_CELL_XY                                   \
@@ -85,7 +103,7 @@ __global__ void k_ref_boundary(GlobalCtx c, DevParams d, const float* __restrict
   WSB_CELL_XY
   float4 b, w;
   char4 wl;
-  boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
+  boundary_cell(GlobalAt{c, x, y}, g, d, initial_T, x, y, b, w, wl);
   baseOut[ci] = b;
   waterOut[ci] = w;
   wallOut[ci] = wl;
