@@ -154,6 +154,27 @@ def full_state(w: int, h: int, seed: int = 7, g: dict | None = None, with_drople
     return base, water, wall, drops
 
 
+def add_clouds(base, water, wall, n_blobs: int = 64, seed: int = 5, cloud_peak: float = 3.0):
+    """Drop Gaussian cloud blobs (cloud water + the same amount of total water) into the air cells
+    of a full-size state, between 25 % and 75 % of the height, so that the precipitation pass has
+    clouds to spawn droplets in (BASELINE config 4).  In place; each blob only touches its own
+    bounding box."""
+    h, w = base.shape[:2]
+    rng = np.random.default_rng(seed)
+    for _ in range(n_blobs):
+        cx, cy = rng.uniform(0, w), rng.uniform(0.25 * h, 0.75 * h)
+        r = rng.uniform(0.02, 0.06) * h
+        x0, x1 = int(max(cx - 3 * r, 0)), int(min(cx + 3 * r, w))
+        y0, y1 = int(max(cy - 3 * r, 1)), int(min(cy + 3 * r, h - 2))
+        if x1 <= x0 or y1 <= y0:
+            continue
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        blob = (np.float32(cloud_peak) * np.exp(-(((xx - cx) ** 2 + (yy - cy) ** 2) / (r * r)))).astype(np.float32)
+        air = wall[y0:y1, x0:x1, 1] != 0
+        water[y0:y1, x0:x1, 1] += np.where(air, blob, 0).astype(np.float32)
+        water[y0:y1, x0:x1, 0] += np.where(air, blob, 0).astype(np.float32)
+
+
 def init_rain_drops(n: int, seed: int = 42) -> np.ndarray:
     """initRainDrops (app.js:4901-4913) with a seeded generator instead of Math.random():
     every droplet starts inactive (water mass in [-10,-9)) and the slots hold RNG seeds."""

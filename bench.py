@@ -343,10 +343,11 @@ def particles_leg(W, H, K, Wm, device_index):
     nd = 1_000_000
     sim = wsb200.Simulation(W, H, nd, device=device_index, gui_controls=g)
     base, water, wall, drops = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=True, n_droplets=nd)
+    wsb200.synth.add_clouds(base, water, wall, n_blobs=96, seed=5)  # something to rain from
     sim.upload(base, water, wall, drops)
     del base, water, wall
     sim.set_profiling(True)
-    sim.step(Wm)
+    sim.step(max(Wm, 30))  # spin-up: the first iterations spawn the bulk of the droplets
     sim.sync()
     sim.step(K)
     sim.sync()

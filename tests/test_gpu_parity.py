@@ -363,3 +363,34 @@ def test_periodic_translation_invariance():
     assert rel_err(np.roll(ga, k, 1), gb, floor=1e-2) < 1e-3
     a.close()
     b.close()
+
+
+def test_upload_local_and_kernel_timers():
+    """wsb_upload_local (padded-strip upload; on one GPU the padded strip is the whole grid),
+    wsb_get_layout and the per-kernel-class event timers used by bench.py."""
+    g, base, water, wall, _ = stress_state(192, 96, seed=29)
+    g["enablePrecipitation"] = False
+    a = make_cuda(g, base, water, wall, None, SIM.SCHEDULE_FUSED)
+    b = wsb200.Simulation(192, 96, 0, gui_controls=g)
+    assert b.layout() == (0, 192, 0) and list(b.padded_columns()) == list(range(192))
+    b.upload_local(base, water, wall)
+    b.set_frame_inputs(P.frame_inputs(g))
+    b.set_profiling(True)
+    a.step(5)
+    b.step(5)
+    assert np.array_equal(a.read_pixels(SIM.FIELD_BASE), b.read_pixels(SIM.FIELD_BASE))
+    ms_pvb, n_pvb = b.kernel_time_ms(SIM.KERNEL_PVB)
+    ms_adv, n_adv = b.kernel_time_ms(SIM.KERNEL_ADV)
+    assert n_pvb == 5 and n_adv == 5 and ms_pvb > 0 and ms_adv > 0
+    assert b.last_step_ms() >= ms_pvb + ms_adv - 1e-3
+    assert b.kernel_time_ms(SIM.KERNEL_DRY) == (0.0, 0)
+    # dry sweeps and full iterations share one canonical state (advection output, pressure pending)
+    a.step_dry(2)
+    a.step(2)
+    b.step_dry(2)
+    b.step(2)
+    assert np.array_equal(a.read_pixels(SIM.FIELD_BASE), b.read_pixels(SIM.FIELD_BASE))
+    with pytest.raises(SIM.WsbError):
+        b.upload_local(base[:, :100], water[:, :100], wall[:, :100])
+    a.close()
+    b.close()
