@@ -2,12 +2,12 @@
 // stencil kernels (+ the particle kernel), and the fused "dry sweep".
 //
 //   k_fused_pvb   pressure(prev iteration) -> velocity -> curl -> vorticity -> boundary
-//                 reads  base_1, wall_1 (tile + 3-cell halo, cp.async into shared memory),
+//                 reads  base_1, wall_1 (tile + 3-cell halo staged in shared memory),
 //                        water_1, light_0 (own cell, prefetched; sparse neighbours), feedback,
 //                        deposition (only after a particle pass)
 //                 writes base_0, water_0, wall_0                      88 (+24) B / cell
 //   k_fused_adv   advection (+ condensation, forcing, wall cells, brush, airplane) -> lighting
-//                 reads  base_0, water_0, wall_0, light_src (tile + 2-cell halo, cp.async)
+//                 reads  base_0, water_0, wall_0, light_src (tile + 2-cell halo staged)
 //                 writes base_1, water_1, wall_1, light_dst           104 B / cell
 //   k_fused_dry   pressure(prev iteration) -> velocity -> advection(base only)   36 B / cell
 //
@@ -15,13 +15,12 @@
 // iteration i+1, so base "after pressure" never travels through HBM; wsb_read_rect materialises it
 // on demand for the rectangle being read.  curl and vortForce never leave shared memory.
 //
-// Staging: every thread issues cp.async (LDGSTS) copies for its share of the tile + halo —
-// 8-byte pieces of the 16-byte AoS cells, so the tile lands in shared memory already split into
-// (vx,vy) / (P,T) / (total,cloud) float2 planes and scalar planes — then one wait + barrier.  All
-// of a CTA's HBM reads are in flight at once and no register is spent on staging.  The periodic
-// wrap of the reference's REPEAT textures only exists on edge tiles (a block-uniform branch).
-// Stencil passes then sweep the staged planes in place; the final per-cell pass gathers with
-// plain shared-memory indices.  A back-trace that leaves the halo (|v| >= 1 cell / iteration, never
+// Staging: every thread loads its share of the tile + halo with coalesced 16-byte loads (several
+// cells in flight per thread) and scatters the channels into per-channel float planes in shared
+// memory (see stage_tile: measured cheaper on the LSU data pipe than cp.async from the AoS source).
+// The periodic wrap of the reference's REPEAT textures only exists on edge tiles (a block-uniform
+// branch).  Stencil passes then sweep the staged planes in place; the final per-cell pass gathers
+// with plain shared-memory indices, one wavefront per gather.  A back-trace that leaves the halo (|v| >= 1 cell / iteration, never
 // seen in the shipped saves) takes an exact, slow global-memory path.
 //
 // TMA (cp.async.bulk.tensor) is deliberately not used: a tensor-map box lands in shared memory in
@@ -39,47 +38,62 @@ constexpr int kNT = 256;  // threads per CTA: thread (tx, ty0) computes rows ty0
 constexpr int kRowStep = kNT / kTX;
 
 // ---------------------------------------------------------------------------------------------
-// cp.async (LDGSTS) helpers
+// Tile staging
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async4(void* s, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_addr(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* s, const void* g) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_addr(s)), "l"(g) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
 __device__ __forceinline__ char4 as_char4(int w) { return *reinterpret_cast<const char4*>(&w); }
+// packed wall word (type | dist << 8 | vert << 16 | veg << 24)
+__device__ __forceinline__ bool wl_is_wall(int w) { return (w & 0xff00) == 0; }            // DISTANCE == 0
+__device__ __forceinline__ bool wl_is_land_wall(int w) { return (w & 0xffff) == 0x0001; }  // DISTANCE == 0 && TYPE == LAND
 
-// Visit every cell of the staged region [X0, X0+SW) x [Y0, Y0+SH): f(s, ci, cil) with s the
-// shared-memory index, ci the global cell index (periodic wrap) and cil the global cell index for
-// the light texture (wrap S = REPEAT, wrap T = CLAMP_TO_EDGE, app.js:5276-5279).
-template <int SW, int SH, class F>
-__device__ __forceinline__ void for_each_staged(const Geom& g, int X0, int Y0, F&& f) {
-  constexpr int N = SW * SH;
+// Stage the region [X0, X0+SW) x [Y0, Y0+SH) of AoS global arrays into per-channel shared-memory
+// planes THROUGH REGISTERS: load(ci, cil) returns the cell's registers (16-byte coalesced loads, 512 B
+// per warp), store(s, regs) scatters the channels with 4-byte stores.  G cells per thread are
+// loaded back to back before the first store, so G x 16..52 B per thread are in flight.
+//   s   shared-memory index of the cell
+//   ci  global cell index with the reference's periodic wrap (REPEAT textures)
+//   cil global cell index for the light texture (wrap S = REPEAT, wrap T = CLAMP_TO_EDGE, app.js:5276-5279)
+// Measured on B200 (profiles/): cp.async from the 16-byte-strided AoS source costs ~2x the LSU
+// data-pipe wavefronts of this path, and float planes make every later gather a single wavefront.
+// The wrap only exists on edge tiles (a block-uniform branch); interior tiles walk (row, column)
+// incrementally without divisions.
+template <int SW, int SH, int G, class Load, class Store>
+__device__ __forceinline__ void stage_tile(const Geom& g, int X0, int Y0, Load load, Store store) {
+  constexpr int N = SW * SH, R = (N + kNT - 1) / kNT;
   const int tid = threadIdx.x;
+  using Regs = decltype(load(0, 0));
   const bool interior = (X0 >= 0) && (X0 + SW <= g.pitch) && (Y0 >= 0) && (Y0 + SH <= g.H);
-  if (interior) {  // block-uniform: no wrap, incremental (row, column) walk without divisions
-    constexpr int DJ = kNT / SW, DI = kNT % SW;
-    int i = tid % SW;
-    int ci = (Y0 + tid / SW) * g.pitch + X0 + i;
-    const int stepA = DJ * g.pitch + DI, stepB = g.pitch - SW;
+  constexpr int DJ = kNT / SW, DI = kNT % SW;
+  int i = tid % SW;
+  int ci = (Y0 + tid / SW) * g.pitch + X0 + i;
+  const int stepA = DJ * g.pitch + DI, stepB = g.pitch - SW;
 #pragma unroll
-    for (int s = tid; s < N; s += kNT) {
-      f(s, ci, ci);
+  for (int r0 = 0; r0 < R; r0 += G) {
+    Regs regs[G];
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const int s = tid + (r0 + k) * kNT;
+      if (r0 + k < R && s < N) {
+        if (interior) {
+          regs[k] = load(ci, ci);
+        } else {
+          const int j = s / SW, ii = s - j * SW;
+          const int xx = wrap_x(g, X0 + ii);
+          regs[k] = load(wrap_y(Y0 + j, g.H) * g.pitch + xx, min(max(Y0 + j, 0), g.H - 1) * g.pitch + xx);
+        }
+      }
       i += DI;
       ci += stepA;
       if (i >= SW) { i -= SW; ci += stepB; }
     }
-  } else {
-    for (int s = tid; s < N; s += kNT) {
-      const int j = s / SW, i = s - j * SW;
-      const int xx = wrap_x(g, X0 + i);
-      f(s, wrap_y(Y0 + j, g.H) * g.pitch + xx, min(max(Y0 + j, 0), g.H - 1) * g.pitch + xx);
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+      const int s = tid + (r0 + k) * kNT;
+      if (r0 + k < R && s < N) store(s, regs[k]);
     }
   }
 }
+
+struct BaseWallRegs { float4 b; int w; };
 
 // ---------------------------------------------------------------------------------------------
 // Exact slow paths (global memory, any coordinates).  __noinline__ with pointer arguments so that
@@ -163,48 +177,51 @@ constexpr int kHD = 2;                   // raw halo: advection +-1 of post-velo
 constexpr int kSWD = kTX + 2 * kHD;      // 68
 constexpr int kSHD = kTY + 2 * kHD;      // 20
 constexpr int kND = kSWD * kSHD;         // 1360
-constexpr size_t kSmemDry = (size_t)kND * (8 + 8 + 8 + 4);  // V, PT raw, PT post-pressure, wall
+constexpr size_t kSmemDry = (size_t)kND * 4 * 6;  // float planes: VX, VY, P, T raw, T post-pressure, wall
 
 // glob: base = base_1 (advection output, pressure pending), wall = wall_1.
 __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d, int applyPressure,
                                                       float4* __restrict__ baseOut, unsigned* __restrict__ maxv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* sV = reinterpret_cast<float2*>(smem_raw);
-  float2* sPT = sV + kND;
-  float2* sPT2 = sPT + kND;
-  int* sWl = reinterpret_cast<int*>(sPT2 + kND);
+  float* sVX = reinterpret_cast<float*>(smem_raw);
+  float* sVY = sVX + kND;
+  float* sP = sVY + kND;
+  float* sT = sP + kND;    // raw T
+  float* sT2 = sT + kND;   // T after the pressure pass
+  int* sWl = reinterpret_cast<int*>(sT2 + kND);
   constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
   const int X0 = g.cx0 + blockIdx.x * kTX - kHD, Y0 = blockIdx.y * kTY - kHD;
 
-  for_each_staged<kSWD, kSHD>(g, X0, Y0, [&](int s, int ci, int) {
-    const float* src = reinterpret_cast<const float*>(glob.base + ci);
-    cp_async8(&sV[s], src);
-    cp_async8(&sPT[s], src + 2);
-    cp_async4(&sWl[s], glob.wall + ci);
-  });
-  cp_async_wait_all();
+  stage_tile<kSWD, kSHD, 6>(
+      g, X0, Y0,
+      [&](int ci, int) { return BaseWallRegs{glob.base[ci], reinterpret_cast<const int*>(glob.wall)[ci]}; },
+      [&](int s, const BaseWallRegs& r) {
+        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
+        sWl[s] = r.w;
+      });
   __syncthreads();
 
-  // pressure pass of the previous iteration (pressureShader.frag); valid for i >= 1, j >= 1
+  // pressure pass of the previous iteration (pressureShader.frag); valid for i >= 1, j >= 1.
+  // P' only reads velocities: in place.  T' reads the raw T below: separate plane.
   for (int s = SW + tid; s < kND; s += kNT) {
-    const float2 v = sV[s];
-    float2 pt = sPT[s];
+    float T = sT[s];
     if (applyPressure) {
-      const char4 wYm = as_char4(sWl[s - SW]);
-      pressure_cell(v.x, v.y, pt.x, pt.y, sV[s - 1].x, sV[s - SW].y, sPT[s - SW].y, wYm.x, wYm.y);
+      if (wl_is_land_wall(sWl[s - SW])) T -= sT[s - SW] - 1000.0f;                       // pressureShader.frag:24-26
+      sP[s] += (sVX[s - 1] - sVX[s] + sVY[s - SW] - sVY[s]) * 0.45f;                    // :42
     }
-    sPT2[s] = pt;
+    sT2[s] = T;
   }
   __syncthreads();
   // velocity (velocityShader.frag), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
   for (int s = SW + tid; s < kND - SW; s += kNT) {
-    float2 v = sV[s];
-    velocity_cell(d, v.x, v.y, sPT2[s].x, sPT2[s + 1].x, sPT2[s + SW].x, (int)as_char4(sWl[s]).y);
-    sV[s] = v;
+    float vx = sVX[s], vy = sVY[s];
+    velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + SW], wl_is_wall(sWl[s]) ? 0 : 1);
+    sVX[s] = vx;
+    sVY[s] = vy;
   }
   __syncthreads();
 
@@ -222,13 +239,13 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
       if (y >= g.H) break;
       const int c = (ty + kHD) * SW + lxBase;
       const float fragCoordY = (float)y + 0.5f;
-      const char4 w0 = as_char4(sWl[c]);
+      const int w0 = sWl[c];
       float4 base;
-      if (w0.y != 0) {
-        const float2 v00 = sV[c];
-        vm = fmaxf(vm, fmaxf(fabsf(v00.x), fabsf(v00.y)));
-        const AdvVel a = adv_velocities(v00.x, v00.y, sV[c - 1].x, sV[c - SW].y, sV[c + 1].y, sV[c + SW].x, sV[c + SW - 1].x,
-                                        sV[c - SW + 1].y);
+      if (!wl_is_wall(w0)) {
+        const float vx00 = sVX[c], vy00 = sVY[c];
+        vm = fmaxf(vm, fmaxf(fabsf(vx00), fabsf(vy00)));
+        const AdvVel a = adv_velocities(vx00, vy00, sVX[c - 1], sVY[c - SW], sVY[c + 1], sVX[c + SW], sVX[c + SW - 1],
+                                        sVY[c - SW + 1]);
         const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
         const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
         const BilerpSetup b3 = bilerp_setup(fragCoordX - a.Px, fragCoordY - a.Py);
@@ -238,21 +255,19 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
         const int l3 = tile_index<SW>(b3, lxBase, gx, Y0, lx3, ly3);
         // post-velocity / post-pressure planes are valid on [1, SW-2] x [1, SH-2]
         if (tile_ok<kSWD, kSHD>(lx1, ly1, 1, 1) && tile_ok<kSWD, kSHD>(lx2, ly2, 1, 1) && tile_ok<kSWD, kSHD>(lx3, ly3, 1, 1)) {
-          base.x = mix2d(sV[l1].x, sV[l1 + 1].x, sV[l1 + SW].x, sV[l1 + SW + 1].x, b1.fx, b1.fx, b1.fy);
-          base.y = mix2d(sV[l2].y, sV[l2 + 1].y, sV[l2 + SW].y, sV[l2 + SW + 1].y, b2.fx, b2.fx, b2.fy);
-          const WallMix m = wall_mix(as_char4(sWl[l3]).y, as_char4(sWl[l3 + 1]).y, as_char4(sWl[l3 + SW]).y,
-                                     as_char4(sWl[l3 + SW + 1]).y, b3.fx, b3.fy);
-          const float2 pa = sPT2[l3], pb = sPT2[l3 + 1], pc = sPT2[l3 + SW], pd = sPT2[l3 + SW + 1];
-          base.z = mix2d(pa.x, pb.x, pc.x, pd.x, m.ab, m.cd, m.abcd);
-          base.w = mix2d(pa.y, pb.y, pc.y, pd.y, m.ab, m.cd, m.abcd);
+          base.x = mix2d(sVX[l1], sVX[l1 + 1], sVX[l1 + SW], sVX[l1 + SW + 1], b1.fx, b1.fx, b1.fy);
+          base.y = mix2d(sVY[l2], sVY[l2 + 1], sVY[l2 + SW], sVY[l2 + SW + 1], b2.fx, b2.fx, b2.fy);
+          const WallMix m = wall_mix(wl_is_wall(sWl[l3]) ? 0 : 1, wl_is_wall(sWl[l3 + 1]) ? 0 : 1, wl_is_wall(sWl[l3 + SW]) ? 0 : 1,
+                                     wl_is_wall(sWl[l3 + SW + 1]) ? 0 : 1, b3.fx, b3.fy);
+          base.z = mix2d(sP[l3], sP[l3 + 1], sP[l3 + SW], sP[l3 + SW + 1], m.ab, m.cd, m.abcd);
+          base.w = mix2d(sT2[l3], sT2[l3 + 1], sT2[l3 + SW], sT2[l3 + SW + 1], m.ab, m.cd, m.abcd);
         } else {
           float vmSlow = 0.0f;  // a local of the cold branch: keeps vm itself in a register
           base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
           vm = fmaxf(vm, vmSlow);
         }
       } else {  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
-        const float2 v = sV[c], pt = sPT2[c];
-        base = make_float4(v.x, v.y, pt.x, (w0.x == WALLTYPE_LAND) ? 1000.0f : pt.y);
+        base = make_float4(sVX[c], sVY[c], sP[c], ((w0 & 0xff) == WALLTYPE_LAND) ? 1000.0f : sT2[c]);
       }
       baseOut[(size_t)y * g.pitch + x] = base;
     }
@@ -267,14 +282,14 @@ constexpr int kH1 = 3;                      // halo of the pressure->boundary ch
 constexpr int kSW1 = kTX + 2 * kH1;         // 70
 constexpr int kSH1 = kTY + 2 * kH1;         // 22
 constexpr int kN1 = kSW1 * kSH1;            // 1540 cells per staged tile
-// V (8) | PT raw, later curl (8) | PT post-pressure (8) | wall (4) | vortForce (8)
-constexpr size_t kSmem1 = (size_t)kN1 * (8 + 8 + 8 + 4 + 8);
+// float planes: VX | VY | P | T raw, later curl | T post-pressure | wall | vortForce x | vortForce y
+constexpr size_t kSmem1 = (size_t)kN1 * 4 * 8;
 
 // boundary_cell context positioned at shared-memory cell c: base / wall / vortForce from the tile,
 // own-cell water / light / feedback / deposition from registers (prefetched), the sparse
 // neighbour fetches of water and light (surface cells only) from HBM.
 struct PvbAt {
-  const float2 *sV, *sPT2, *sVF;
+  const float *sVX, *sVY, *sP, *sT2, *sVFX, *sVFY;
   const int* sWl;
   int c;
   const GlobalCtx& glob;
@@ -283,14 +298,14 @@ struct PvbAt {
   float2 light0, dep0;
   __device__ __forceinline__ int si(int dx, int dy) const { return c + dy * kSW1 + dx; }
   __device__ __forceinline__ float4 base4(int dx, int dy) const {
-    const float2 v = sV[si(dx, dy)], pt = sPT2[si(dx, dy)];
-    return make_float4(v.x, v.y, pt.x, pt.y);
+    const int s = si(dx, dy);
+    return make_float4(sVX[s], sVY[s], sP[s], sT2[s]);
   }
-  __device__ __forceinline__ float bx(int dx, int dy) const { return sV[si(dx, dy)].x; }
-  __device__ __forceinline__ float by(int dx, int dy) const { return sV[si(dx, dy)].y; }
-  __device__ __forceinline__ float bt(int dx, int dy) const { return sPT2[si(dx, dy)].y; }
+  __device__ __forceinline__ float bx(int dx, int dy) const { return sVX[si(dx, dy)]; }
+  __device__ __forceinline__ float by(int dx, int dy) const { return sVY[si(dx, dy)]; }
+  __device__ __forceinline__ float bt(int dx, int dy) const { return sT2[si(dx, dy)]; }
   __device__ __forceinline__ char4 wall4(int dx, int dy) const { return as_char4(sWl[si(dx, dy)]); }
-  __device__ __forceinline__ float2 vort(int dx, int dy) const { return sVF[si(dx, dy)]; }
+  __device__ __forceinline__ float2 vort(int dx, int dy) const { return make_float2(sVFX[si(dx, dy)], sVFY[si(dx, dy)]); }
   __device__ __forceinline__ float4 water4(int dx, int dy) const {
     if (dx == 0 && dy == 0) return water0;
     return glob.water[glob.idx_near(x + dx, y + dy)];
@@ -312,27 +327,23 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
                                                       float4* fb, float2* dep, float4* __restrict__ baseOut,
                                                       float4* __restrict__ waterOut, char4* __restrict__ wallOut) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* sV = reinterpret_cast<float2*>(smem_raw);
-  float2* sPT = sV + kN1;                           // raw (P, T); dead after the pressure sweep
-  float* sCurl = reinterpret_cast<float*>(sPT);     // ... then curl
-  float2* sPT2 = sPT + kN1;                         // post-pressure (P, T)
-  int* sWl = reinterpret_cast<int*>(sPT2 + kN1);
-  float2* sVF = reinterpret_cast<float2*>(sWl + kN1);
+  float* sVX = reinterpret_cast<float*>(smem_raw);
+  float* sVY = sVX + kN1;
+  float* sP = sVY + kN1;
+  float* sT = sP + kN1;      // raw T; dead after the pressure sweep ...
+  float* sCurl = sT;         // ... then curl
+  float* sT2 = sT + kN1;     // T after the pressure pass
+  int* sWl = reinterpret_cast<int*>(sT2 + kN1);
+  float* sVFX = reinterpret_cast<float*>(sWl + kN1);
+  float* sVFY = sVFX + kN1;
   constexpr int SW = kSW1;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
   const int X0 = g.cx0 + blockIdx.x * kTX - kH1, Y0 = blockIdx.y * kTY - kH1;
 
-  for_each_staged<kSW1, kSH1>(g, X0, Y0, [&](int s, int ci, int) {
-    const float* src = reinterpret_cast<const float*>(glob.base + ci);
-    cp_async8(&sV[s], src);
-    cp_async8(&sPT[s], src + 2);
-    cp_async4(&sWl[s], glob.wall + ci);
-  });
-
-  // own-cell operands of the boundary pass: first row now (in flight during the sweeps below),
-  // the following rows one step ahead of their use
+  // own-cell operands of the boundary pass: first row now (in flight during staging and the
+  // sweeps below), the following rows one step ahead of their use
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kH1 + tx;
   const bool colOk = x < g.cx1;
@@ -352,44 +363,51 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   };
   prefetch(ty0);
 
-  cp_async_wait_all();
+  stage_tile<kSW1, kSH1, 4>(
+      g, X0, Y0,
+      [&](int ci, int) { return BaseWallRegs{glob.base[ci], reinterpret_cast<const int*>(glob.wall)[ci]}; },
+      [&](int s, const BaseWallRegs& r) {
+        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
+        sWl[s] = r.w;
+      });
   __syncthreads();
 
-  // S1: pressure pass of the previous iteration; valid for i >= 1, j >= 1
+  // S1: pressure pass of the previous iteration; valid for i >= 1, j >= 1.  P' only reads
+  // velocities: in place.  T' reads the raw T below: separate plane.
   for (int s = SW + tid; s < kN1; s += kNT) {
-    const float2 v = sV[s];
-    float2 pt = sPT[s];
+    float T = sT[s];
     if (applyPressure) {
-      const char4 wYm = as_char4(sWl[s - SW]);
-      pressure_cell(v.x, v.y, pt.x, pt.y, sV[s - 1].x, sV[s - SW].y, sPT[s - SW].y, wYm.x, wYm.y);
+      if (wl_is_land_wall(sWl[s - SW])) T -= sT[s - SW] - 1000.0f;     // pressureShader.frag:24-26
+      sP[s] += (sVX[s - 1] - sVX[s] + sVY[s - SW] - sVY[s]) * 0.45f;  // :42
     }
-    sPT2[s] = pt;
+    sT2[s] = T;
   }
   __syncthreads();
   // S2: velocity in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
   for (int s = SW + tid; s < kN1 - SW; s += kNT) {
-    float2 v = sV[s];
-    velocity_cell(d, v.x, v.y, sPT2[s].x, sPT2[s + 1].x, sPT2[s + SW].x, (int)as_char4(sWl[s]).y);
-    sV[s] = v;
+    float vx = sVX[s], vy = sVY[s];
+    velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + SW], wl_is_wall(sWl[s]) ? 0 : 1);
+    sVX[s] = vx;
+    sVY[s] = vy;
   }
   __syncthreads();
-  // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw PT plane is dead: reuse it)
-  for (int s = SW + tid; s < kN1 - 2 * SW; s += kNT) {
-    const float2 v = sV[s];
-    sCurl[s] = curl_cell(v.x, v.y, sV[s + SW].x, sV[s + 1].y);
-  }
+  // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
+  for (int s = SW + tid; s < kN1 - 2 * SW; s += kNT) sCurl[s] = curl_cell(sVX[s], sVY[s], sVX[s + SW], sVY[s + 1]);
   __syncthreads();
   // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
   // valid for 2 <= i <= SW-4
-  for (int s = (kH1 - 1) * SW + tid; s < (kH1 + kTY) * SW; s += kNT)
-    sVF[s] = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - SW], sCurl[s + 1], sCurl[s + SW]);
+  for (int s = (kH1 - 1) * SW + tid; s < (kH1 + kTY) * SW; s += kNT) {
+    const float2 vf = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - SW], sCurl[s + 1], sCurl[s + SW]);
+    sVFX[s] = vf.x;
+    sVFY[s] = vf.y;
+  }
   __syncthreads();
 
   // S5: boundary pass on the TX x TY interior
 #pragma unroll 1
   for (int ty = ty0; ty < kTY; ty += kRowStep) {
     const int y = Y0 + kH1 + ty;
-    PvbAt c{sV, sPT2, sVF, sWl, (ty + kH1) * SW + tx + kH1, glob, x, y, waterN, fbN, lightN, depN};
+    PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kH1, glob, x, y, waterN, fbN, lightN, depN};
     prefetch(ty + kRowStep);
     if (colOk && y < g.H) {
       float4 b, w;
@@ -414,8 +432,8 @@ constexpr int kH2 = 2;                  // halo: covers every back-trace with |v
 constexpr int kSW2 = kTX + 2 * kH2;     // 68
 constexpr int kSH2 = kTY + 2 * kH2;     // 20
 constexpr int kN2 = kSW2 * kSH2;        // 1360
-// V 8 | PT 8 | water(total, cloud) 8 | precip 4 | smoke 4 | wall 4 | light: sun 4, IR down 4, IR up 4
-constexpr size_t kSmem2 = (size_t)kN2 * (8 + 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4);
+// float planes: VX VY P T | water total, cloud, precip, smoke | wall | light: sun, IR down, IR up
+constexpr size_t kSmem2 = (size_t)kN2 * 4 * 12;
 
 // light fetches of lighting_cell from the staged light planes (rows are staged with the
 // CLAMP_TO_EDGE rule, so the clamped row lighting_cell passes maps straight to a tile row)
@@ -428,6 +446,8 @@ struct TileLightCtx {
   __device__ __forceinline__ float lightIRup(int x, int y) const { return sLU[si(x, y)]; }
 };
 
+struct AdvRegs { float4 b, w, l; int wl; };
+
 // glob: base_0, water_0, wall_0 (boundary output), light = light_src.
 __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
@@ -437,10 +457,13 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
                                                       char4* __restrict__ wallOut, float4* __restrict__ lightOut,
                                                       unsigned* __restrict__ maxv) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* sV = reinterpret_cast<float2*>(smem_raw);
-  float2* sPT = sV + kN2;
-  float2* sW01 = sPT + kN2;
-  float* sW2 = reinterpret_cast<float*>(sW01 + kN2);
+  float* sVX = reinterpret_cast<float*>(smem_raw);
+  float* sVY = sVX + kN2;
+  float* sP = sVY + kN2;
+  float* sT = sP + kN2;
+  float* sW0 = sT + kN2;
+  float* sW1 = sW0 + kN2;
+  float* sW2 = sW1 + kN2;
   float* sW3 = sW2 + kN2;
   int* sWl = reinterpret_cast<int*>(sW3 + kN2);
   float* sLS = reinterpret_cast<float*>(sWl + kN2);
@@ -452,21 +475,15 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
   const int tid = threadIdx.x;
   const int X0 = g.cx0 + blockIdx.x * kTX - kH2, Y0 = blockIdx.y * kTY - kH2;
 
-  for_each_staged<kSW2, kSH2>(g, X0, Y0, [&](int s, int ci, int cil) {
-    const float* bsrc = reinterpret_cast<const float*>(glob.base + ci);
-    const float* wsrc = reinterpret_cast<const float*>(glob.water + ci);
-    const float* lsrc = reinterpret_cast<const float*>(glob.light + cil);
-    cp_async8(&sV[s], bsrc);
-    cp_async8(&sPT[s], bsrc + 2);
-    cp_async8(&sW01[s], wsrc);
-    cp_async4(&sW2[s], wsrc + 2);
-    cp_async4(&sW3[s], wsrc + 3);
-    cp_async4(&sWl[s], glob.wall + ci);
-    cp_async4(&sLS[s], lsrc);
-    cp_async4(&sLD[s], lsrc + 2);
-    cp_async4(&sLU[s], lsrc + 3);
-  });
-  cp_async_wait_all();
+  stage_tile<kSW2, kSH2, 2>(
+      g, X0, Y0,
+      [&](int ci, int cil) { return AdvRegs{glob.base[ci], glob.water[ci], glob.light[cil], reinterpret_cast<const int*>(glob.wall)[ci]}; },
+      [&](int s, const AdvRegs& r) {
+        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
+        sW0[s] = r.w.x; sW1[s] = r.w.y; sW2[s] = r.w.z; sW3[s] = r.w.w;
+        sWl[s] = r.wl;
+        sLS[s] = r.l.x; sLD[s] = r.l.z; sLU[s] = r.l.w;
+      });
   __syncthreads();
 
   const TileLightCtx lc{sLS, sLD, sLU, X0, Y0};
@@ -487,14 +504,14 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       const float texCoordY = fragCoordY * g.texelY;
       const char4 w0 = as_char4(sWl[c]);
       int wType = w0.x, wDist = w0.y, wVert = w0.z, wVeg = w0.w;
-      const int aboveDist = as_char4(sWl[c + SW]).y;
+      const int aboveDist = wl_is_wall(sWl[c + SW]) ? 0 : 1;  // only ever tested against 0
       float4 base, water;
       char4 wl;
       bool done = false;
       if (wDist != 0) {  // air: semi-Lagrangian gathers from the tile
-        const float2 v00 = sV[c];
-        const AdvVel a = adv_velocities(v00.x, v00.y, sV[c - 1].x, sV[c - SW].y, sV[c + 1].y, sV[c + SW].x, sV[c + SW - 1].x,
-                                        sV[c - SW + 1].y);
+        const float vx00 = sVX[c], vy00 = sVY[c];
+        const AdvVel a = adv_velocities(vx00, vy00, sVX[c - 1], sVY[c - SW], sVY[c + 1], sVX[c + SW], sVX[c + SW - 1],
+                                        sVY[c - SW + 1]);
         const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
         const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
         const float posPx = fragCoordX - a.Px, posPy = fragCoordY - a.Py;
@@ -507,23 +524,21 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
         const int l4 = tile_index<SW>(b4, lxBase, gx, Y0, lx4, ly4);
         if (tile_ok<kSW2, kSH2>(lx1, ly1, 0, 0) && tile_ok<kSW2, kSH2>(lx2, ly2, 0, 0) && tile_ok<kSW2, kSH2>(lx3, ly3, 0, 0) &&
             tile_ok<kSW2, kSH2>(lx4, ly4, 0, 0)) {
-          vm = fmaxf(vm, fmaxf(fabsf(v00.x), fabsf(v00.y)));
-          base.x = mix2d(sV[l1].x, sV[l1 + 1].x, sV[l1 + SW].x, sV[l1 + SW + 1].x, b1.fx, b1.fx, b1.fy);
-          base.y = mix2d(sV[l2].y, sV[l2 + 1].y, sV[l2 + SW].y, sV[l2 + SW + 1].y, b2.fx, b2.fx, b2.fy);
+          vm = fmaxf(vm, fmaxf(fabsf(vx00), fabsf(vy00)));
+          base.x = mix2d(sVX[l1], sVX[l1 + 1], sVX[l1 + SW], sVX[l1 + SW + 1], b1.fx, b1.fx, b1.fy);
+          base.y = mix2d(sVY[l2], sVY[l2 + 1], sVY[l2 + SW], sVY[l2 + SW + 1], b2.fx, b2.fx, b2.fy);
           {
-            const WallMix m = wall_mix(as_char4(sWl[l3]).y, as_char4(sWl[l3 + 1]).y, as_char4(sWl[l3 + SW]).y,
-                                       as_char4(sWl[l3 + SW + 1]).y, b3.fx, b3.fy);
-            const float2 pa = sPT[l3], pb = sPT[l3 + 1], pc = sPT[l3 + SW], pd = sPT[l3 + SW + 1];
-            base.z = mix2d(pa.x, pb.x, pc.x, pd.x, m.ab, m.cd, m.abcd);
-            base.w = mix2d(pa.y, pb.y, pc.y, pd.y, m.ab, m.cd, m.abcd);
-            const float2 qa = sW01[l3], qb = sW01[l3 + 1], qc = sW01[l3 + SW], qd = sW01[l3 + SW + 1];
-            water.x = mix2d(qa.x, qb.x, qc.x, qd.x, m.ab, m.cd, m.abcd);
-            water.y = mix2d(qa.y, qb.y, qc.y, qd.y, m.ab, m.cd, m.abcd);
+            const WallMix m = wall_mix(wl_is_wall(sWl[l3]) ? 0 : 1, wl_is_wall(sWl[l3 + 1]) ? 0 : 1, wl_is_wall(sWl[l3 + SW]) ? 0 : 1,
+                                       wl_is_wall(sWl[l3 + SW + 1]) ? 0 : 1, b3.fx, b3.fy);
+            base.z = mix2d(sP[l3], sP[l3 + 1], sP[l3 + SW], sP[l3 + SW + 1], m.ab, m.cd, m.abcd);
+            base.w = mix2d(sT[l3], sT[l3 + 1], sT[l3 + SW], sT[l3 + SW + 1], m.ab, m.cd, m.abcd);
+            water.x = mix2d(sW0[l3], sW0[l3 + 1], sW0[l3 + SW], sW0[l3 + SW + 1], m.ab, m.cd, m.abcd);
+            water.y = mix2d(sW1[l3], sW1[l3 + 1], sW1[l3 + SW], sW1[l3 + SW + 1], m.ab, m.cd, m.abcd);
             water.w = mix2d(sW3[l3], sW3[l3 + 1], sW3[l3 + SW], sW3[l3 + SW + 1], m.ab, m.cd, m.abcd);
           }
           {
-            const WallMix m = wall_mix(as_char4(sWl[l4]).y, as_char4(sWl[l4 + 1]).y, as_char4(sWl[l4 + SW]).y,
-                                       as_char4(sWl[l4 + SW + 1]).y, b4.fx, b4.fy);
+            const WallMix m = wall_mix(wl_is_wall(sWl[l4]) ? 0 : 1, wl_is_wall(sWl[l4 + 1]) ? 0 : 1, wl_is_wall(sWl[l4 + SW]) ? 0 : 1,
+                                       wl_is_wall(sWl[l4 + SW + 1]) ? 0 : 1, b4.fx, b4.fy);
             water.z = mix2d(sW2[l4], sW2[l4 + 1], sW2[l4 + SW], sW2[l4 + SW + 1], m.ab, m.cd, m.abcd);
           }
           adv_air_thermo(g, d, sndT, sndW, sndV, texCoordY, base, water);
@@ -537,10 +552,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
           done = true;
         }
       } else {  // wall: pass-through + surface processes
-        const float2 v = sV[c], pt = sPT[c], w01 = sW01[c];
-        base = make_float4(v.x, v.y, pt.x, pt.y);
-        water = make_float4(w01.x, w01.y, sW2[c], sW3[c]);
-        adv_wall_cell<false>(d, texCoordY, wType, aboveDist, sPT[c + SW].y, wVeg, base, water);
+        base = make_float4(sVX[c], sVY[c], sP[c], sT[c]);
+        water = make_float4(sW0[c], sW1[c], sW2[c], sW3[c]);
+        adv_wall_cell<false>(d, texCoordY, wType, aboveDist, sT[c + SW], wVeg, base, water);
       }
       if (!done) {
         adv_user_input(g, d, initial_T, texCoordX, texCoordY, aboveDist, wType, wDist, wVert, wVeg, base, water);
@@ -559,10 +573,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
         const char4 wb = as_char4(sWl[cb]);
         if (wb.y == 0) {  // the usual case: a wall cell, whose advection is a local update
           int tB = wb.x, dB = wb.y, vB = wb.w;
-          const float2 vb = sV[cb], ptb = sPT[cb], w01b = sW01[cb];
-          float4 bb = make_float4(vb.x, vb.y, ptb.x, ptb.y), wtb = make_float4(w01b.x, w01b.y, sW2[cb], sW3[cb]);
+          float4 bb = make_float4(sVX[cb], sVY[cb], sP[cb], sT[cb]), wtb = make_float4(sW0[cb], sW1[cb], sW2[cb], sW3[cb]);
           const float texCoordYb = ((float)wrap_y(y - 1, g.H) + 0.5f) * g.texelY;
-          adv_wall_cell<false>(d, texCoordYb, tB, w0.y, sPT[c].y, vB, bb, wtb);
+          adv_wall_cell<false>(d, texCoordYb, tB, w0.y, sT[c], vB, bb, wtb);
           adv_user_input(g, d, initial_T, texCoordX, texCoordYb, w0.y, tB, dB, wb.z, vB, bb, wtb);
           TBelow = bb.w;
         } else {

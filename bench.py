@@ -116,6 +116,7 @@ def _oracle_sample(width_cols: int, height: int):
     g = P.resolve_settings(None)
     g["enablePrecipitation"] = False
     base, water, wall, _ = wsb200.synth.full_state(GRID_W, height, seed=7, g=g, with_droplets=False, cols=np.arange(width_cols))
+    O.set_threads()  # all host cores (torchrun exports OMP_NUM_THREADS=1)
     ora = O.OracleSim(width_cols, height, 0)
     ora.upload(base, water, wall, None)
     ora.set_params(P.derive_params(g))
@@ -135,7 +136,9 @@ def cpu_baseline(budget_s: float = 12.0):
     t = time.perf_counter()
     ora.step(n)
     dt = time.perf_counter() - t
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    from oracle import oracle as O
+
+    cores = O.lib().oracle_get_threads()
     return {"value": cols * h * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{cols}x{h} periodic slab of the bench state (full physics, no particles), {n} iterations, OpenMP over rows; "
                       "CPU restatement of the reference shaders (oracle/wsb_oracle.cpp) — the reference itself (GLSL under a browser) cannot run here"}
@@ -152,7 +155,9 @@ def run_reference(args):
     ora.step(args.steps)
     dt = time.perf_counter() - t
     value = cols * h * args.steps / dt
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    from oracle import oracle as O
+
+    cores = O.lib().oracle_get_threads()
     sample = (f"each step = one iteration on a {cols}x{h} periodic slab of the 16384x4096 bench state; value = slab cells x steps / time; "
               "oracle/wsb_oracle.cpp (C++/OpenMP restatement of the reference shaders; the GLSL/browser reference cannot be executed on this box)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,

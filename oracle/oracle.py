@@ -62,10 +62,20 @@ def lib():
         L.oracle_random2d.argtypes = [ctypes.c_float, ctypes.c_float]
         L.oracle_map_rangeC.restype = ctypes.c_float
         L.oracle_map_rangeC.argtypes = [ctypes.c_float] * 5
+        L.oracle_set_threads.argtypes = [ctypes.c_int]
+        L.oracle_get_threads.restype = ctypes.c_int
         L.oracle_hash.restype = ctypes.c_uint32
         L.oracle_hash.argtypes = [ctypes.c_uint32]
         _lib = L
     return _lib
+
+
+def set_threads(n: int | None = None) -> int:
+    """Use n OpenMP threads (default: every core this process may run on); returns the team size."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_threads(int(n))
+    return lib().oracle_get_threads()
 
 
 def _ptr(a):

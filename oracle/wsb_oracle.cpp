@@ -17,6 +17,8 @@
 //
 // Citations: paths are relative to the reference checkout; "common" = shaders/common.glsl.
 
+#include <omp.h>
+
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -1272,6 +1274,10 @@ int oracle_get_even(void* h) { return ((Sim*)h)->even ? 1 : 0; }
 int oracle_last_drops(void* h) { return ((Sim*)h)->last_drops; }
 float oracle_get_inactive(void* h) { return ((Sim*)h)->inactiveDroplets; }
 void oracle_set_inactive(void* h, float v) { ((Sim*)h)->inactiveDroplets = v; }
+
+// OpenMP team size (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core)
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_threads() { return omp_get_max_threads(); }
 
 // unit-test hooks for the helpers
 float oracle_maxWater(float T) { return maxWater(T); }
