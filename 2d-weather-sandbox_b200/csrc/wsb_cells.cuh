@@ -452,19 +452,25 @@ __device__ __forceinline__ void adv_air_thermo(const Geom& g, const DevParams& d
   realTemp += dT;
   water.y += condensation;
   if (texCoordY > p.globalEffectsStartAlt && texCoordY < p.globalEffectsEndAlt) {  // :154-181
-    water.x -= gclamp(p.globalDrying, 0.0f, gmax(water.x - maxWater(gmax(realTemp - 20.0f, CtoK(-80.0f))), 0.0f));
-    base.w += p.globalHeating;
-    int si = (int)(texCoordY * (1.0f / g.ltexelY));
-    int sm = max(si - 1, 0);
-    float Tdiff = base.w - (sndT[si] + sndT[sm]) / 2.0f;
-    base.w -= Tdiff * 0.001f * p.soundingForcing;
-    float Wdiff = water.x - (sndW[si] + sndW[sm]) / 2.0f;
-    water.x -= Wdiff * 0.001f * p.soundingForcing;
-    float dragK = 1.0f - map_rangeC(p.soundingForcing, 0.1f, 1.0f, 0.0f, 0.001f);
-    base.x *= dragK;
-    base.y *= dragK;
-    float velDiff = base.x - (sndV[si] + sndV[sm]) / 2.0f;
-    base.x -= velDiff * map_rangeC(p.soundingForcing, 0.9f, 1.0f, 0.0f, 0.001f);
+    // Each sub-block is skipped when its (uniform) rate is exactly +0: the skipped update then is
+    // x -= +0 / x += +0 / x *= 1, which returns x itself for every finite x (the GUI defaults are
+    // all zero, so the idle simulation pays for none of this).
+    if (__float_as_uint(p.globalDrying) != 0u)
+      water.x -= gclamp(p.globalDrying, 0.0f, gmax(water.x - maxWater(gmax(realTemp - 20.0f, CtoK(-80.0f))), 0.0f));
+    if (__float_as_uint(p.globalHeating) != 0u) base.w += p.globalHeating;
+    if (__float_as_uint(p.soundingForcing) != 0u) {
+      int si = (int)(texCoordY * (1.0f / g.ltexelY));
+      int sm = max(si - 1, 0);
+      float Tdiff = base.w - (sndT[si] + sndT[sm]) / 2.0f;
+      base.w -= Tdiff * 0.001f * p.soundingForcing;
+      float Wdiff = water.x - (sndW[si] + sndW[sm]) / 2.0f;
+      water.x -= Wdiff * 0.001f * p.soundingForcing;
+      float dragK = 1.0f - map_rangeC(p.soundingForcing, 0.1f, 1.0f, 0.0f, 0.001f);
+      base.x *= dragK;
+      base.y *= dragK;
+      float velDiff = base.x - (sndV[si] + sndV[sm]) / 2.0f;
+      base.x -= velDiff * map_rangeC(p.soundingForcing, 0.9f, 1.0f, 0.0f, 0.001f);
+    }
   }
   water.x = gmax(water.x, 0.0f);  // :187
 }

@@ -321,7 +321,7 @@ struct PvbAt {
 // glob: base = base_1, wall = wall_1, water = water_1, light = light_0 (glob.fb / glob.dep unused).
 // useFb: feedback / deposition hold data from the last particle pass; the kernel consumes them and
 // writes the zeros of the reference's gl.clear (app.js:5933-5934) back to the cells that were hit.
-__global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
+__global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
                                                       const float* __restrict__ initial_T, int applyPressure, int useFb,
                                                       float4* fb, float2* dep, float4* __restrict__ baseOut,
@@ -558,7 +558,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       }
       if (!done) {
         adv_user_input(g, d, initial_T, texCoordX, texCoordY, aboveDist, wType, wDist, wVert, wVeg, base, water);
-        wl = pack_wall(wType, wDist, wVert, wVeg);
+        // idle frame: the wall texel passes through unchanged (in-range bytes need no saturation)
+        if (wType == w0.x && wDist == w0.y && wVeg == w0.w) wl = w0;
+        else wl = pack_wall(wType, wDist, wVert, wVeg);
       }
       const size_t ci = (size_t)y * g.pitch + x;
       baseOut[ci] = base;

@@ -394,3 +394,32 @@ def test_upload_local_and_kernel_timers():
         b.upload_local(base[:, :100], water[:, :100], wall[:, :100])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
+def test_global_effects_and_sounding_forcing(schedule):
+    """advectionShader.frag:154-181 with every rate non-zero and real sounding profiles (the fused
+    kernels skip each sub-block when its uniform is exactly zero, so the idle tests never enter it)."""
+    w, h = 160, 96
+    g, base, water, wall, _ = stress_state(w, h, seed=31)
+    g["enablePrecipitation"] = False
+    g["globalDrying"], g["globalHeating"], g["soundingForcing"] = 2e-5, -3e-4, 0.95
+    g["globalEffectsStartAlt"], g["globalEffectsEndAlt"] = 1500, 9000
+    t0 = P.initial_T_profile(h, g)
+    rng = np.random.default_rng(1)
+    snd_T = (t0 + rng.normal(0, 1.0, h + 1)).astype(np.float32)
+    snd_W = np.abs(rng.normal(3.0, 1.0, h + 1)).astype(np.float32)
+    snd_V = rng.normal(0.0, 0.05, h + 1).astype(np.float32)
+    sim = make_cuda(g, base, water, wall, None, schedule)
+    ora = make_oracle(g, base, water, wall, None)
+    sim.set_profiles(t0, snd_T, snd_W, snd_V)
+    ora.set_profiles(t0, snd_T, snd_W, snd_V)
+    sim.step(12)
+    ora.step(12)
+    _assert_fields_equal(sim, ora, f"global effects, schedule {schedule}", exact=True)
+    # and they really changed the result
+    idle = make_cuda(dict(g, globalDrying=0.0, globalHeating=0.0, soundingForcing=0.0), base, water, wall, None, schedule)
+    idle.step(12)
+    assert not np.array_equal(idle.read_pixels(SIM.FIELD_BASE), sim.read_pixels(SIM.FIELD_BASE))
+    sim.close()
+    idle.close()
