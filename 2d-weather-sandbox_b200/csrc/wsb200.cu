@@ -164,6 +164,9 @@ struct wsb_sim {
   std::vector<Span> spans;
 
   // multi-GPU
+  cudaStream_t comm_stream = nullptr;       // halo exchange runs here, beside the next boundary kernel
+  cudaEvent_t evCompute = nullptr, evExch = nullptr;
+  bool exch_pending = false;                // an exchange is in flight on comm_stream
   void* comm = nullptr;
   unsigned char *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
   size_t halo_bytes = 0;
@@ -207,63 +210,82 @@ int check_launch(wsb_sim* s, const char* what) {
   do { if (check_launch(s, what)) return 1; } while (0)
 
 // --- per-kernel timing -----------------------------------------------------------------------
-size_t prof_mark(wsb_sim* s) {
+size_t prof_mark(wsb_sim* s, cudaStream_t st) {
   if (s->ev_used == s->ev_pool.size()) {
     cudaEvent_t e;
     cudaEventCreate(&e);
     s->ev_pool.push_back(e);
   }
-  cudaEventRecord(s->ev_pool[s->ev_used], s->stream);
+  cudaEventRecord(s->ev_pool[s->ev_used], st);
   return s->ev_used++;
 }
-struct ProfScope {  // brackets the launches of one kernel class
-  wsb_sim* s; int kind; size_t e0;
-  ProfScope(wsb_sim* s_, int k) : s(s_), kind(k), e0(0) { if (s->profiling) e0 = prof_mark(s); }
-  ~ProfScope() { if (s->profiling) s->spans.push_back({kind, e0, prof_mark(s)}); }
+struct ProfScope {  // brackets the launches of one kernel class on one stream
+  wsb_sim* s; int kind; size_t e0; cudaStream_t st;
+  ProfScope(wsb_sim* s_, int k, cudaStream_t st_ = nullptr) : s(s_), kind(k), e0(0), st(st_ ? st_ : s_->stream) {
+    if (s->profiling) e0 = prof_mark(s, st);
+  }
+  ~ProfScope() { if (s->profiling) s->spans.push_back({kind, e0, prof_mark(s, st)}); }
 };
 
 // --- halo exchange ---------------------------------------------------------------------------
 struct HaloField { void* ptr; int elt; };
 
+// Ghost-column exchange on comm_stream, ordered after everything enqueued on the compute stream
+// so far.  It stays in flight (exch_pending) until join_exchange() makes the compute stream wait
+// for it — the next iteration's interior tiles run beside it.
 int exchange(wsb_sim* s, const std::vector<HaloField>& fields) {
   if (s->cfg.n_ranks <= 1) return 0;
-  ProfScope prof(s, WSB_KERNEL_HALO);
-  const int n = s->H * kGhost;
-  const int threads = 256, blocks = (n + threads - 1) / threads;
-  size_t off = 0;
-  for (const HaloField& f : fields) {
-    if (f.elt == 16)
-      k_pack_halo<float4><<<blocks, threads, 0, s->stream>>>((const float4*)f.ptr, s->pitch, s->H, s->lw,
-                                                             (float4*)(s->sendL + off), (float4*)(s->sendR + off));
-    else
-      k_pack_halo<int><<<blocks, threads, 0, s->stream>>>((const int*)f.ptr, s->pitch, s->H, s->lw,
-                                                          (int*)(s->sendL + off), (int*)(s->sendR + off));
-    LAUNCHED("k_pack_halo");
-    off += (size_t)n * f.elt;
+  cudaStream_t cs = s->comm_stream;
+  CK(cudaEventRecord(s->evCompute, s->stream));
+  CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
+  {
+    ProfScope prof(s, WSB_KERNEL_HALO, cs);
+    const int n = s->H * kGhost;
+    const int threads = 256, blocks = (n + threads - 1) / threads;
+    size_t off = 0;
+    for (const HaloField& f : fields) {
+      if (f.elt == 16)
+        k_pack_halo<float4><<<blocks, threads, 0, cs>>>((const float4*)f.ptr, s->pitch, s->H, s->lw, (float4*)(s->sendL + off),
+                                                         (float4*)(s->sendR + off));
+      else
+        k_pack_halo<int><<<blocks, threads, 0, cs>>>((const int*)f.ptr, s->pitch, s->H, s->lw, (int*)(s->sendL + off),
+                                                      (int*)(s->sendR + off));
+      LAUNCHED("k_pack_halo");
+      off += (size_t)n * f.elt;
+    }
+    if (off > s->halo_bytes) return fail("halo staging overflow");
+    const int left = (s->cfg.rank + s->cfg.n_ranks - 1) % s->cfg.n_ranks;
+    const int right = (s->cfg.rank + 1) % s->cfg.n_ranks;
+    // Sends go (left, right); receives are posted (right, left) so that with two ranks — where both
+    // neighbours are the same peer and NCCL matches operations in call order — the block a rank
+    // sends to its left neighbour lands in that neighbour's RIGHT ghost zone.
+    NCK(g_nccl.GroupStart());
+    NCK(g_nccl.Send(s->sendL, off, kNcclChar, left, s->comm, cs));
+    NCK(g_nccl.Send(s->sendR, off, kNcclChar, right, s->comm, cs));
+    NCK(g_nccl.Recv(s->recvR, off, kNcclChar, right, s->comm, cs));
+    NCK(g_nccl.Recv(s->recvL, off, kNcclChar, left, s->comm, cs));
+    NCK(g_nccl.GroupEnd());
+    s->launches++;
+    off = 0;
+    for (const HaloField& f : fields) {
+      if (f.elt == 16)
+        k_unpack_halo<float4><<<blocks, threads, 0, cs>>>((float4*)f.ptr, s->pitch, s->H, s->lw, (const float4*)(s->recvL + off),
+                                                           (const float4*)(s->recvR + off));
+      else
+        k_unpack_halo<int><<<blocks, threads, 0, cs>>>((int*)f.ptr, s->pitch, s->H, s->lw, (const int*)(s->recvL + off),
+                                                        (const int*)(s->recvR + off));
+      LAUNCHED("k_unpack_halo");
+      off += (size_t)n * f.elt;
+    }
   }
-  if (off > s->halo_bytes) return fail("halo staging overflow");
-  const int left = (s->cfg.rank + s->cfg.n_ranks - 1) % s->cfg.n_ranks;
-  const int right = (s->cfg.rank + 1) % s->cfg.n_ranks;
-  // Sends go (left, right); receives are posted (right, left) so that with two ranks — where both
-  // neighbours are the same peer and NCCL matches operations in call order — the block a rank
-  // sends to its left neighbour lands in that neighbour's RIGHT ghost zone.
-  NCK(g_nccl.GroupStart());
-  NCK(g_nccl.Send(s->sendL, off, kNcclChar, left, s->comm, s->stream));
-  NCK(g_nccl.Send(s->sendR, off, kNcclChar, right, s->comm, s->stream));
-  NCK(g_nccl.Recv(s->recvR, off, kNcclChar, right, s->comm, s->stream));
-  NCK(g_nccl.Recv(s->recvL, off, kNcclChar, left, s->comm, s->stream));
-  NCK(g_nccl.GroupEnd());
-  s->launches++;
-  off = 0;
-  for (const HaloField& f : fields) {
-    if (f.elt == 16)
-      k_unpack_halo<float4><<<blocks, threads, 0, s->stream>>>((float4*)f.ptr, s->pitch, s->H, s->lw,
-                                                               (const float4*)(s->recvL + off), (const float4*)(s->recvR + off));
-    else
-      k_unpack_halo<int><<<blocks, threads, 0, s->stream>>>((int*)f.ptr, s->pitch, s->H, s->lw,
-                                                            (const int*)(s->recvL + off), (const int*)(s->recvR + off));
-    LAUNCHED("k_unpack_halo");
-    off += (size_t)n * f.elt;
+  CK(cudaEventRecord(s->evExch, cs));
+  s->exch_pending = true;
+  return 0;
+}
+int join_exchange(wsb_sim* s) {
+  if (s->exch_pending) {
+    CK(cudaStreamWaitEvent(s->stream, s->evExch, 0));
+    s->exch_pending = false;
   }
   return 0;
 }
@@ -366,10 +388,25 @@ int fused_iteration(wsb_sim* s) {
   // feedback / deposition cells it has consumed (app.js:5933-5934 folded in)
   {
     ProfScope prof(s, WSB_KERNEL_PVB);
-    k_fused_pvb<<<tile_grid(s), kNT, kSmem1, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->initial_T,
-                                                           s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
-                                                           s->base[0], s->water[0], s->wall[0]);
-    LAUNCHED("k_fused_pvb");
+    GlobalCtx c = make_ctx(s, 1, 1, 1, 0);
+    auto launch_pvb = [&](int cx0, int cx1) {
+      c.g.cx0 = cx0;
+      c.g.cx1 = cx1;
+      k_fused_pvb<<<dim3((cx1 - cx0 + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, s->stream>>>(
+          c, s->dp, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep, s->base[0], s->water[0], s->wall[0]);
+      return check_launch(s, "k_fused_pvb");
+    };
+    // While the previous iteration's ghost exchange is still in flight, run the tiles whose staged
+    // region (tile + 3 columns) stays clear of the ghost columns; then wait, then the two edges.
+    const int innerEnd = kTX + ((s->pitch - (kGhost + kH1) - kTX) / kTX) * kTX;
+    if (s->exch_pending && innerEnd > kTX) {
+      if (launch_pvb(kTX, innerEnd)) return 1;
+      if (join_exchange(s)) return 1;
+      if (launch_pvb(0, kTX) || launch_pvb(innerEnd, s->pitch)) return 1;
+    } else {
+      if (join_exchange(s)) return 1;
+      if (launch_pvb(0, s->pitch)) return 1;
+    }
   }
   s->fb_dirty = false;
   // advection (+ condensation ...) -> lighting
@@ -405,7 +442,7 @@ int dry_iteration(wsb_sim* s) {
     }
     std::swap(s->base[0], s->base[1]);
     s->pressure_pending = true;
-    if (exchange(s, {{s->base[1], 16}})) return 1;
+    if (exchange(s, {{s->base[1], 16}}) || join_exchange(s)) return 1;
   }
   s->iter++;
   return 0;
@@ -568,6 +605,14 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
     if ((rc = alloc_all(s))) break;
     if ((rc = zero_transients(s))) break;
     if (cfg->n_ranks > 1) {
+      int prLo = 0, prHi = 0;  // exchange kernels are tiny: let them cut in front of the queued stencil CTAs
+      cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+      if ((e = cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prHi)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evExch, cudaEventDisableTiming)) != cudaSuccess) {
+        rc = fail("wsb_create: %s", cudaGetErrorString(e));
+        break;
+      }
       if ((rc = load_nccl())) break;
       Id128 id;
       memcpy(id.internal, cfg->comm_id, WSB_COMM_ID_BYTES);
@@ -586,7 +631,11 @@ int wsb_destroy(wsb_sim* s) {
   if (!s) return 0;
   cudaSetDevice(s->cfg.device);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
   if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+  if (s->evCompute) cudaEventDestroy(s->evCompute);
+  if (s->evExch) cudaEventDestroy(s->evExch);
+  if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
   for (int k = 0; k < 2; k++) {
     cudaFree(s->base[k]); cudaFree(s->water[k]); cudaFree(s->wall[k]); cudaFree(s->light[k]); cudaFree(s->drops[k]);
   }
@@ -686,6 +735,7 @@ int wsb_step(wsb_sim* s, int32_t n_iters) {
   for (int i = 0; i < n_iters; i++) {
     if (s->schedule == WSB_SCHEDULE_REFERENCE ? ref_iteration(s) : fused_iteration(s)) return 1;
   }
+  if (join_exchange(s)) return 1;  // everything enqueued so far is ordered on the compute stream again
   CK(cudaEventRecord(s->ev1, s->stream));
   s->timed = true;
   return 0;
