@@ -1,8 +1,10 @@
 // wsb200.cu — host side of libwsb200.so: the C ABI of include/wsb200.h over the sm_100a kernels.
 //
-// One wsb_sim = one process / one GPU.  State lives in HBM in exactly the reference's packed
-// texture layouts (base / water / light RGBA32F, wall RGBA8I, feedback RGBA32F, deposition RG32F,
-// droplets 5 x f32), row 0 = bottom row, x fastest.  A multi-GPU run cuts the grid into x-strips,
+// One wsb_sim = one process / one GPU.  The C ABI speaks exactly the reference's packed texture
+// layouts (base / water / light RGBA32F, wall RGBA8I, feedback RGBA32F, deposition RG32F, droplets
+// 5 x f32; row 0 = bottom row, x fastest).  In HBM every channel of base / water / light is its own
+// float plane (wsb_ref_kernels.cuh) — upload and readback transpose on the device — so that the
+// fused kernels can stage tiles with one TMA box per plane.  A multi-GPU run cuts the grid into x-strips,
 // one per rank, each stored with kGhost ghost columns on both sides; the ring of ranks refreshes
 // the ghost columns once per iteration with ncclSend/ncclRecv over NVLink (x is periodic, so rank
 // 0 and rank N-1 are neighbours).
@@ -105,24 +107,37 @@ int load_nccl() {
 // halo pack / unpack: ghost columns are strided in the x-fastest layout; they travel as
 // contiguous [side][row][kGhost] blocks.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void k_pack_halo(const T* __restrict__ f, int pitch, int H, int lw, T* __restrict__ toLeft,
-                            T* __restrict__ toRight) {
+constexpr int kMaxHaloPlanes = 16;
+struct HaloPlanes { int* p[kMaxHaloPlanes]; int n; };  // every exchanged plane has 4-byte elements
+
+// staging block layout: [plane][row][kGhost]
+__global__ void k_pack_halo(HaloPlanes hp, int pitch, int H, int lw, int* __restrict__ toLeft, int* __restrict__ toRight) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= H * kGhost) return;
-  const int y = t / kGhost, i = t - y * kGhost;
+  const int per = H * kGhost;
+  if (t >= per * hp.n) return;
+  const int k = t / per, r = t - k * per;
+  const int y = r / kGhost, i = r - y * kGhost;
+  const int* f = hp.p[k];
   toLeft[t] = f[(size_t)y * pitch + kGhost + i];   // my leftmost owned columns
   toRight[t] = f[(size_t)y * pitch + lw + i];      // my rightmost owned columns
 }
-template <typename T>
-__global__ void k_unpack_halo(T* __restrict__ f, int pitch, int H, int lw, const T* __restrict__ fromLeft,
-                              const T* __restrict__ fromRight) {
+__global__ void k_unpack_halo(HaloPlanes hp, int pitch, int H, int lw, const int* __restrict__ fromLeft,
+                              const int* __restrict__ fromRight) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= H * kGhost) return;
-  const int y = t / kGhost, i = t - y * kGhost;
+  const int per = H * kGhost;
+  if (t >= per * hp.n) return;
+  const int k = t / per, r = t - k * per;
+  const int y = r / kGhost, i = r - y * kGhost;
+  int* f = hp.p[k];
   f[(size_t)y * pitch + i] = fromLeft[t];
   f[(size_t)y * pitch + kGhost + lw + i] = fromRight[t];
 }
+
+// cuTensorMapEncodeTiled, resolved through the runtime (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
 
 }  // namespace
 
@@ -136,8 +151,14 @@ struct wsb_sim {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
 
-  float4 *base[2] = {}, *water[2] = {}, *light[2] = {}, *fb = nullptr;
-  char4* wall[2] = {};
+  // one RGBA32F texture = four float planes, with the TMA descriptors of each plane for the two
+  // box shapes the fused kernels stage (tile + 2-cell halo: dry / advection; tile + 3: boundary)
+  struct Field { Planes4 p; CUtensorMap map2[4], map3[4]; };
+  Field base[2] = {}, water[2] = {}, light[2] = {};
+  int* wall[2] = {};
+  CUtensorMap wallMap2[2], wallMap3[2];
+  bool use_tma = false;
+  float4* fb = nullptr;
   float2 *dep = nullptr, *vort = nullptr;
   float* curl = nullptr;
   float* drops[2] = {};
@@ -178,11 +199,11 @@ size_t cells(const wsb_sim* s) { return (size_t)s->pitch * s->H; }
 
 GlobalCtx make_ctx(const wsb_sim* s, int b, int w, int wl, int l) {
   GlobalCtx c;
-  c.base = s->base[b];
-  c.water = s->water[w];
+  c.base = s->base[b].p;
+  c.water = s->water[w].p;
   c.wall = s->wall[wl];
   c.vortf = s->vort;
-  c.light = s->light[l];
+  c.light = s->light[l].p;
   c.fb = s->fb;
   c.dep = s->dep;
   c.g = s->g;
@@ -228,55 +249,39 @@ struct ProfScope {  // brackets the launches of one kernel class on one stream
 };
 
 // --- halo exchange ---------------------------------------------------------------------------
-struct HaloField { void* ptr; int elt; };
-
+void add_planes(HaloPlanes& hp, const Planes4& f) {
+  for (int k = 0; k < 4; k++) hp.p[hp.n++] = reinterpret_cast<int*>(f.c[k]);
+}
 // Ghost-column exchange on comm_stream, ordered after everything enqueued on the compute stream
 // so far.  It stays in flight (exch_pending) until join_exchange() makes the compute stream wait
 // for it — the next iteration's interior tiles run beside it.
-int exchange(wsb_sim* s, const std::vector<HaloField>& fields) {
+int exchange(wsb_sim* s, const HaloPlanes& hp) {
   if (s->cfg.n_ranks <= 1) return 0;
   cudaStream_t cs = s->comm_stream;
   CK(cudaEventRecord(s->evCompute, s->stream));
   CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
   {
     ProfScope prof(s, WSB_KERNEL_HALO, cs);
-    const int n = s->H * kGhost;
+    const int n = s->H * kGhost * hp.n;
+    const size_t bytes = (size_t)n * 4;
+    if (bytes > s->halo_bytes) return fail("halo staging overflow");
     const int threads = 256, blocks = (n + threads - 1) / threads;
-    size_t off = 0;
-    for (const HaloField& f : fields) {
-      if (f.elt == 16)
-        k_pack_halo<float4><<<blocks, threads, 0, cs>>>((const float4*)f.ptr, s->pitch, s->H, s->lw, (float4*)(s->sendL + off),
-                                                         (float4*)(s->sendR + off));
-      else
-        k_pack_halo<int><<<blocks, threads, 0, cs>>>((const int*)f.ptr, s->pitch, s->H, s->lw, (int*)(s->sendL + off),
-                                                      (int*)(s->sendR + off));
-      LAUNCHED("k_pack_halo");
-      off += (size_t)n * f.elt;
-    }
-    if (off > s->halo_bytes) return fail("halo staging overflow");
+    k_pack_halo<<<blocks, threads, 0, cs>>>(hp, s->pitch, s->H, s->lw, (int*)s->sendL, (int*)s->sendR);
+    LAUNCHED("k_pack_halo");
     const int left = (s->cfg.rank + s->cfg.n_ranks - 1) % s->cfg.n_ranks;
     const int right = (s->cfg.rank + 1) % s->cfg.n_ranks;
     // Sends go (left, right); receives are posted (right, left) so that with two ranks — where both
     // neighbours are the same peer and NCCL matches operations in call order — the block a rank
     // sends to its left neighbour lands in that neighbour's RIGHT ghost zone.
     NCK(g_nccl.GroupStart());
-    NCK(g_nccl.Send(s->sendL, off, kNcclChar, left, s->comm, cs));
-    NCK(g_nccl.Send(s->sendR, off, kNcclChar, right, s->comm, cs));
-    NCK(g_nccl.Recv(s->recvR, off, kNcclChar, right, s->comm, cs));
-    NCK(g_nccl.Recv(s->recvL, off, kNcclChar, left, s->comm, cs));
+    NCK(g_nccl.Send(s->sendL, bytes, kNcclChar, left, s->comm, cs));
+    NCK(g_nccl.Send(s->sendR, bytes, kNcclChar, right, s->comm, cs));
+    NCK(g_nccl.Recv(s->recvR, bytes, kNcclChar, right, s->comm, cs));
+    NCK(g_nccl.Recv(s->recvL, bytes, kNcclChar, left, s->comm, cs));
     NCK(g_nccl.GroupEnd());
     s->launches++;
-    off = 0;
-    for (const HaloField& f : fields) {
-      if (f.elt == 16)
-        k_unpack_halo<float4><<<blocks, threads, 0, cs>>>((float4*)f.ptr, s->pitch, s->H, s->lw, (const float4*)(s->recvL + off),
-                                                           (const float4*)(s->recvR + off));
-      else
-        k_unpack_halo<int><<<blocks, threads, 0, cs>>>((int*)f.ptr, s->pitch, s->H, s->lw, (const int*)(s->recvL + off),
-                                                        (const int*)(s->recvR + off));
-      LAUNCHED("k_unpack_halo");
-      off += (size_t)n * f.elt;
-    }
+    k_unpack_halo<<<blocks, threads, 0, cs>>>(hp, s->pitch, s->H, s->lw, (const int*)s->recvL, (const int*)s->recvR);
+    LAUNCHED("k_unpack_halo");
   }
   CK(cudaEventRecord(s->evExch, cs));
   s->exch_pending = true;
@@ -294,7 +299,7 @@ int join_exchange(wsb_sim* s) {
 const dim3 kRefBlock(64, 4);
 
 int ref_velocity(wsb_sim* s) {
-  k_ref_velocity<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 0, 0, 0, 0), s->dp, s->base[1], s->wall[1]);
+  k_ref_velocity<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 0, 0, 0, 0), s->dp, s->base[1].p, s->wall[1]);
   LAUNCHED("k_ref_velocity");
   return 0;
 }
@@ -310,8 +315,8 @@ int ref_vorticity(wsb_sim* s) {
 }
 int ref_boundary(wsb_sim* s) {
   set_iter_uniform(s);
-  k_ref_boundary<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->initial_T, s->base[0],
-                                                                s->water[0], s->wall[0]);
+  k_ref_boundary<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->initial_T, s->base[0].p,
+                                                                s->water[0].p, s->wall[0]);
   LAUNCHED("k_ref_boundary");
   return 0;
 }
@@ -319,21 +324,21 @@ int ref_advection(wsb_sim* s, bool dry) {
   GlobalCtx c = make_ctx(s, 0, 0, 0, 0);
   if (dry)
     k_ref_advection<true><<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(c, s->dp, s->initial_T, s->sndT, s->sndW, s->sndV,
-                                                                         s->base[1], s->water[1], s->wall[1], s->maxv);
+                                                                         s->base[1].p, s->water[1].p, s->wall[1], s->maxv);
   else
     k_ref_advection<false><<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(c, s->dp, s->initial_T, s->sndT, s->sndW, s->sndV,
-                                                                          s->base[1], s->water[1], s->wall[1], s->maxv);
+                                                                          s->base[1].p, s->water[1].p, s->wall[1], s->maxv);
   LAUNCHED("k_ref_advection");
   return 0;
 }
 int ref_pressure(wsb_sim* s) {
-  k_ref_pressure<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->base[0], s->wall[0]);
+  k_ref_pressure<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->base[0].p, s->wall[0]);
   LAUNCHED("k_ref_pressure");
   return 0;
 }
 int ref_lighting(wsb_sim* s) {
   const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;  // app.js:5912-5926
-  k_ref_lighting<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, src), s->dp, s->light[dst]);
+  k_ref_lighting<<<grid2d(s, 64, 4), kRefBlock, 0, s->stream>>>(make_ctx(s, 1, 1, 1, src), s->dp, s->light[dst].p);
   LAUNCHED("k_ref_lighting");
   s->even = !s->even;
   return 0;
@@ -359,7 +364,7 @@ int precipitation(wsb_sim* s) {
   set_iter_uniform(s);
   ProfScope prof(s, WSB_KERNEL_PRECIP);
   const int threads = 256, blocks = (s->ND + threads - 1) / threads;
-  k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1], s->water[1], s->fb, s->dep,
+  k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1].p, s->water[1].p, s->fb, s->dep,
                                                      s->lightning, s->inactive, s->g, s->dp, s->ND);
   LAUNCHED("k_precipitation");
   s->fb_dirty = true;
@@ -389,16 +394,20 @@ int fused_iteration(wsb_sim* s) {
   {
     ProfScope prof(s, WSB_KERNEL_PVB);
     GlobalCtx c = make_ctx(s, 1, 1, 1, 0);
+    TileMaps<5> maps;
+    for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].map3[k];
+    maps.m[4] = s->wallMap3[1];
     auto launch_pvb = [&](int cx0, int cx1) {
       c.g.cx0 = cx0;
       c.g.cx1 = cx1;
       k_fused_pvb<<<dim3((cx1 - cx0 + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, s->stream>>>(
-          c, s->dp, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep, s->base[0], s->water[0], s->wall[0]);
+          c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
+          s->base[0].p, s->water[0].p, s->wall[0]);
       return check_launch(s, "k_fused_pvb");
     };
     // While the previous iteration's ghost exchange is still in flight, run the tiles whose staged
-    // region (tile + 3 columns) stays clear of the ghost columns; then wait, then the two edges.
-    const int innerEnd = kTX + ((s->pitch - (kGhost + kH1) - kTX) / kTX) * kTX;
+    // region (tile + 4 columns) stays clear of the ghost columns; then wait, then the two edges.
+    const int innerEnd = kTX + ((s->pitch - (kGhost + kHX) - kTX) / kTX) * kTX;
     if (s->exch_pending && innerEnd > kTX) {
       if (launch_pvb(kTX, innerEnd)) return 1;
       if (join_exchange(s)) return 1;
@@ -412,14 +421,31 @@ int fused_iteration(wsb_sim* s) {
   // advection (+ condensation ...) -> lighting
   {
     ProfScope prof(s, WSB_KERNEL_ADV);
-    k_fused_adv<<<tile_grid(s), kNT, kSmem2, s->stream>>>(make_ctx(s, 0, 0, 0, src), s->dp, s->initial_T, s->sndT, s->sndW,
-                                                           s->sndV, s->base[1], s->water[1], s->wall[1], s->light[dst], s->maxv);
+    TileMaps<12> maps;
+    for (int k = 0; k < 4; k++) {
+      maps.m[k] = s->base[0].map2[k];
+      maps.m[4 + k] = s->water[0].map2[k];
+    }
+    maps.m[8] = s->wallMap2[0];
+    maps.m[9] = s->light[src].map2[0];   // SUNLIGHT
+    maps.m[10] = s->light[src].map2[2];  // IR_DOWN
+    maps.m[11] = s->light[src].map2[3];  // IR_UP
+    k_fused_adv<<<tile_grid(s), kNT, kSmem2, s->stream>>>(make_ctx(s, 0, 0, 0, src), s->dp, maps, s->use_tma ? 1 : 0, s->initial_T,
+                                                           s->sndT, s->sndW, s->sndV, s->base[1].p, s->water[1].p, s->wall[1],
+                                                           s->light[dst].p, s->maxv);
     LAUNCHED("k_fused_adv");
   }
   s->even = !s->even;
   s->pressure_pending = true;
   if (particles && precipitation(s)) return 1;
-  if (exchange(s, {{s->base[1], 16}, {s->water[1], 16}, {s->wall[1], 4}, {s->light[dst], 16}})) return 1;
+  if (s->cfg.n_ranks > 1) {
+    HaloPlanes hp{};
+    add_planes(hp, s->base[1].p);
+    add_planes(hp, s->water[1].p);
+    hp.p[hp.n++] = s->wall[1];
+    add_planes(hp, s->light[dst].p);
+    if (exchange(s, hp)) return 1;
+  }
   s->iter++;
   return 0;
 }
@@ -436,25 +462,65 @@ int dry_iteration(wsb_sim* s) {
     // same canonical state as the full fused schedule: base_1 = advection output, pressure pending
     {
       ProfScope prof(s, WSB_KERNEL_DRY);
-      k_fused_dry<<<tile_grid(s), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, s->pressure_pending ? 1 : 0,
-                                                               s->base[0], s->maxv);
+      TileMaps<5> maps;
+      for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].map2[k];
+      maps.m[4] = s->wallMap2[1];
+      k_fused_dry<<<tile_grid(s), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0,
+                                                               s->pressure_pending ? 1 : 0, s->base[0].p, s->maxv);
       LAUNCHED("k_fused_dry");
     }
     std::swap(s->base[0], s->base[1]);
     s->pressure_pending = true;
-    if (exchange(s, {{s->base[1], 16}}) || join_exchange(s)) return 1;
+    if (s->cfg.n_ranks > 1) {
+      HaloPlanes hp{};
+      add_planes(hp, s->base[1].p);
+      if (exchange(s, hp) || join_exchange(s)) return 1;
+    }
   }
   s->iter++;
   return 0;
 }
 
+// TMA descriptor of one [H][pitch] 4-byte plane with a (boxW x boxH) box; out-of-range elements read 0
+int make_map(wsb_sim* s, CUtensorMap* m, void* plane, bool isInt, int boxW, int boxH) {
+  const cuuint64_t dims[2] = {(cuuint64_t)s->pitch, (cuuint64_t)s->H};
+  const cuuint64_t strides[1] = {(cuuint64_t)s->pitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, isInt ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int alloc_field(wsb_sim* s, wsb_sim::Field& f) {
+  const size_t n = cells(s);
+  for (int k = 0; k < 4; k++) {
+    CK(cudaMalloc(&f.p.c[k], n * sizeof(float)));
+    if (s->use_tma && (make_map(s, &f.map2[k], f.p.c[k], false, kSW2, kSH2) || make_map(s, &f.map3[k], f.p.c[k], false, kSW1, kSH1))) return 1;
+  }
+  return 0;
+}
+
 int alloc_all(wsb_sim* s) {
   const size_t n = cells(s);
+  // TMA needs 16-byte row strides and at least one box per dimension; anything else is staged through registers
+  s->use_tma = false;
+  if (s->pitch % 4 == 0 && s->pitch >= kSW1 && s->H >= kSH1) {
+    if (!g_encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        g_encode = (EncodeTiledFn)fn;
+      cudaGetLastError();
+    }
+    s->use_tma = g_encode != nullptr;
+  }
   for (int k = 0; k < 2; k++) {
-    CK(cudaMalloc(&s->base[k], n * sizeof(float4)));
-    CK(cudaMalloc(&s->water[k], n * sizeof(float4)));
-    CK(cudaMalloc(&s->wall[k], n * sizeof(char4)));
-    CK(cudaMalloc(&s->light[k], n * sizeof(float4)));
+    if (alloc_field(s, s->base[k]) || alloc_field(s, s->water[k]) || alloc_field(s, s->light[k])) return 1;
+    CK(cudaMalloc(&s->wall[k], n * sizeof(int)));
+    if (s->use_tma && (make_map(s, &s->wallMap2[k], s->wall[k], true, kSW2, kSH2) || make_map(s, &s->wallMap3[k], s->wall[k], true, kSW1, kSH1))) return 1;
     if (s->ND) CK(cudaMalloc(&s->drops[k], (size_t)s->ND * 5 * sizeof(float)));
   }
   CK(cudaMalloc(&s->fb, n * sizeof(float4)));
@@ -476,7 +542,7 @@ int alloc_all(wsb_sim* s) {
   CK(cudaMalloc(&s->inactive, 4));
   CK(cudaMalloc(&s->maxv, 4));
   if (s->cfg.n_ranks > 1) {
-    s->halo_bytes = (size_t)s->H * kGhost * (16 + 16 + 4 + 16);
+    s->halo_bytes = (size_t)s->H * kGhost * 4 * 13;  // base 4 + water 4 + wall 1 + light 4 planes
     CK(cudaMalloc(&s->sendL, s->halo_bytes));
     CK(cudaMalloc(&s->sendR, s->halo_bytes));
     CK(cudaMalloc(&s->recvL, s->halo_bytes));
@@ -485,9 +551,22 @@ int alloc_all(wsb_sim* s) {
   return 0;
 }
 
+int need_scratch(wsb_sim* s, size_t ncells) {
+  if (ncells > s->scratch_cells) {
+    CK(cudaStreamSynchronize(s->stream));
+    cudaFree(s->scratch);
+    s->scratch = nullptr;
+    s->scratch_cells = 0;
+    CK(cudaMalloc(&s->scratch, ncells * sizeof(float4)));
+    s->scratch_cells = ncells;
+  }
+  return 0;
+}
+
 int zero_transients(wsb_sim* s) {
   const size_t n = cells(s);
-  for (int k = 0; k < 2; k++) CK(cudaMemsetAsync(s->light[k], 0, n * sizeof(float4), s->stream));
+  for (int k = 0; k < 2; k++)
+    for (int ch = 0; ch < 4; ch++) CK(cudaMemsetAsync(s->light[k].p.c[ch], 0, n * sizeof(float), s->stream));
   CK(cudaMemsetAsync(s->fb, 0, n * sizeof(float4), s->stream));
   CK(cudaMemsetAsync(s->dep, 0, n * sizeof(float2), s->stream));
   if (s->curl) CK(cudaMemsetAsync(s->curl, 0, n * sizeof(float), s->stream));
@@ -518,6 +597,20 @@ int upload_field(wsb_sim* s, void* dst, const void* src, size_t elt) {
   return 0;
 }
 
+// packed RGBA32F texels on the host -> channel planes of copy 0 (through the texel scratch buffer)
+int upload_texels(wsb_sim* s, const Planes4& dst, const float* src, bool global_array) {
+  const size_t n = cells(s);
+  if (need_scratch(s, n)) return 1;
+  if (global_array) {
+    if (upload_field(s, s->scratch, src, 16)) return 1;
+  } else {
+    CK(cudaMemcpyAsync(s->scratch, src, n * 16, cudaMemcpyHostToDevice, s->stream));
+  }
+  k_texels_to_planes<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->scratch, n, dst);
+  LAUNCHED("k_texels_to_planes");
+  return 0;
+}
+
 int use_device(const wsb_sim* s) {
   CK(cudaSetDevice(s->cfg.device));
   return 0;
@@ -532,7 +625,7 @@ const char* wsb_last_error(void) { return g_err; }
 
 const char* wsb_build_info(void) {
   return "libwsb200 abi " "1" " | sm_100a | nvcc " __VERSION__ " | fmad=false | tile "
-         "64x16, 256 threads | ghost 8";
+         "64x16, 256 threads, TMA-staged channel planes | ghost 8";
 }
 
 int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]) {
@@ -637,7 +730,8 @@ int wsb_destroy(wsb_sim* s) {
   if (s->evExch) cudaEventDestroy(s->evExch);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
   for (int k = 0; k < 2; k++) {
-    cudaFree(s->base[k]); cudaFree(s->water[k]); cudaFree(s->wall[k]); cudaFree(s->light[k]); cudaFree(s->drops[k]);
+    for (int ch = 0; ch < 4; ch++) { cudaFree(s->base[k].p.c[ch]); cudaFree(s->water[k].p.c[ch]); cudaFree(s->light[k].p.c[ch]); }
+    cudaFree(s->wall[k]); cudaFree(s->drops[k]);
   }
   cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
   cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
@@ -656,8 +750,10 @@ namespace {
 // a device->device duplicate
 int finish_upload(wsb_sim* s, const float* drops) {
   const size_t n = cells(s);
-  CK(cudaMemcpyAsync(s->base[1], s->base[0], n * 16, cudaMemcpyDeviceToDevice, s->stream));
-  CK(cudaMemcpyAsync(s->water[1], s->water[0], n * 16, cudaMemcpyDeviceToDevice, s->stream));
+  for (int ch = 0; ch < 4; ch++) {
+    CK(cudaMemcpyAsync(s->base[1].p.c[ch], s->base[0].p.c[ch], n * 4, cudaMemcpyDeviceToDevice, s->stream));
+    CK(cudaMemcpyAsync(s->water[1].p.c[ch], s->water[0].p.c[ch], n * 4, cudaMemcpyDeviceToDevice, s->stream));
+  }
   CK(cudaMemcpyAsync(s->wall[1], s->wall[0], n * 4, cudaMemcpyDeviceToDevice, s->stream));
   if (s->ND) {
     CK(cudaMemcpyAsync(s->drops[0], drops, (size_t)s->ND * 20, cudaMemcpyHostToDevice, s->stream));
@@ -672,18 +768,19 @@ int finish_upload(wsb_sim* s, const float* drops) {
 int wsb_upload(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
   if (!s || !base || !water || !wall) return fail("wsb_upload: null argument");
   if (s->ND > 0 && !drops) return fail("wsb_upload: droplets required (n_droplets = %d)", s->ND);
-  if (use_device(s)) return 1;
-  if (upload_field(s, s->base[0], base, 16) || upload_field(s, s->water[0], water, 16) || upload_field(s, s->wall[0], wall, 4)) return 1;
+  if (use_device(s) || join_exchange(s)) return 1;
+  if (upload_texels(s, s->base[0].p, base, true) || upload_texels(s, s->water[0].p, water, true) ||
+      upload_field(s, s->wall[0], wall, 4))
+    return 1;
   return finish_upload(s, drops);
 }
 
 int wsb_upload_local(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
   if (!s || !base || !water || !wall) return fail("wsb_upload_local: null argument");
   if (s->ND > 0 && !drops) return fail("wsb_upload_local: droplets required (n_droplets = %d)", s->ND);
-  if (use_device(s)) return 1;
+  if (use_device(s) || join_exchange(s)) return 1;
   const size_t n = cells(s);
-  CK(cudaMemcpyAsync(s->base[0], base, n * 16, cudaMemcpyHostToDevice, s->stream));
-  CK(cudaMemcpyAsync(s->water[0], water, n * 16, cudaMemcpyHostToDevice, s->stream));
+  if (upload_texels(s, s->base[0].p, base, false) || upload_texels(s, s->water[0].p, water, false)) return 1;
   CK(cudaMemcpyAsync(s->wall[0], wall, n * 4, cudaMemcpyHostToDevice, s->stream));
   return finish_upload(s, drops);
 }
@@ -787,20 +884,21 @@ int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y,
   if (view < WSB_VIEW_FRAMEBUFF_0 || view > WSB_VIEW_LATEST) return fail("wsb_read_rect: unknown view %d", view);
   if (use_device(s)) return 1;
   const bool fused = s->schedule == WSB_SCHEDULE_FUSED;
-  const void* src = nullptr;
+  const void* src = nullptr;        // packed array fields
+  const Planes4* planes = nullptr;  // channel-plane fields
   size_t elt = 0;
   bool pressure_on_the_fly = false;
   const int v1 = view == WSB_VIEW_FRAMEBUFF_1 ? 1 : 0;
   switch (field) {
     case WSB_FIELD_BASE:
       elt = 16;
-      if (fused) { src = s->base[1]; pressure_on_the_fly = (v1 == 0) && s->pressure_pending; }
-      else src = s->base[v1];
+      if (fused) { planes = &s->base[1].p; pressure_on_the_fly = (v1 == 0) && s->pressure_pending; }
+      else planes = &s->base[v1].p;
       break;
     case WSB_FIELD_WATER:
       elt = 16;
       // FUSED before the first iteration: both copies still hold the upload
-      src = s->water[v1];
+      planes = &s->water[v1].p;
       break;
     case WSB_FIELD_WALL:
       elt = 4;
@@ -809,7 +907,7 @@ int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y,
       break;
     case WSB_FIELD_LIGHT:
       elt = 16;
-      src = view == WSB_VIEW_LATEST ? s->light[s->even ? 0 : 1] : s->light[v1];
+      planes = view == WSB_VIEW_LATEST ? &s->light[s->even ? 0 : 1].p : &s->light[v1].p;
       break;
     case WSB_FIELD_FEEDBACK: elt = 16; src = s->fb; break;
     case WSB_FIELD_DEPOSITION: elt = 8; src = s->dep; break;
@@ -826,19 +924,16 @@ int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y,
   if (gx1 <= gx0) { CK(cudaStreamSynchronize(s->stream)); return 0; }
   const int lx0 = gx0 - s->x_begin + s->ghost, cw = gx1 - gx0;
   char* d = (char*)dst + (size_t)(gx0 - x) * elt;
-  if (pressure_on_the_fly) {
-    const size_t need = (size_t)cw * h;
-    if (need > s->scratch_cells) {
-      CK(cudaStreamSynchronize(s->stream));
-      cudaFree(s->scratch);
-      s->scratch = nullptr;
-      s->scratch_cells = 0;
-      CK(cudaMalloc(&s->scratch, need * sizeof(float4)));
-      s->scratch_cells = need;
-    }
+  if (planes) {  // planes -> packed texels in the scratch buffer -> host
+    if (need_scratch(s, (size_t)cw * h)) return 1;
     dim3 b(32, 8), gr((cw + 31) / 32, (h + 7) / 8);
-    k_pressure_rect<<<gr, b, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), lx0, y, cw, h, s->scratch);
-    LAUNCHED("k_pressure_rect");
+    if (pressure_on_the_fly) {
+      k_pressure_rect<<<gr, b, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), lx0, y, cw, h, s->scratch);
+      LAUNCHED("k_pressure_rect");
+    } else {
+      k_planes_to_texels<<<gr, b, 0, s->stream>>>(*planes, s->pitch, lx0, y, cw, h, s->scratch);
+      LAUNCHED("k_planes_to_texels");
+    }
     CK(cudaMemcpy2DAsync(d, (size_t)w * elt, s->scratch, (size_t)cw * elt, (size_t)cw * elt, h, cudaMemcpyDeviceToHost, s->stream));
   } else {
     const char* sp = (const char*)src + ((size_t)y * s->pitch + lx0) * elt;

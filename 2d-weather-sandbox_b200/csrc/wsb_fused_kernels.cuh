@@ -15,18 +15,20 @@
 // iteration i+1, so base "after pressure" never travels through HBM; wsb_read_rect materialises it
 // on demand for the rectangle being read.  curl and vortForce never leave shared memory.
 //
-// Staging: every thread loads its share of the tile + halo with coalesced 16-byte loads (several
-// cells in flight per thread) and scatters the channels into per-channel float planes in shared
-// memory (see stage_tile: measured cheaper on the LSU data pipe than cp.async from the AoS source).
-// The periodic wrap of the reference's REPEAT textures only exists on edge tiles (a block-uniform
-// branch).  Stencil passes then sweep the staged planes in place; the final per-cell pass gathers
-// with plain shared-memory indices, one wavefront per gather.  A back-trace that leaves the halo (|v| >= 1 cell / iteration, never
-// seen in the shipped saves) takes an exact, slow global-memory path.
-//
-// TMA (cp.async.bulk.tensor) is deliberately not used: a tensor-map box lands in shared memory in
-// the AoS global layout (the gathers want channel planes: 4x fewer shared-memory wavefronts) and
-// cannot apply the periodic wrap at the domain edge; see DESIGN.md.
+// Staging: the state lives in HBM as per-channel float planes (wsb_ref_kernels.cuh), so ONE elected
+// thread per CTA issues one TMA box load (cp.async.bulk.tensor.2d -> UTMALDG) per plane: tile + halo
+// land in shared memory as dense [rows][columns] float planes, signalled through an mbarrier with
+// the expected byte count.  No thread spends an instruction, a register or an LSU wavefront on
+// staging, and all of a CTA's HBM reads are in flight at once.  Tiles that need the periodic wrap
+// of the reference's REPEAT textures (the outermost ring of tiles) — or grids whose row pitch is
+// not a multiple of 16 bytes — take a register-staged fallback (stage_tile) with explicit wrap.
+// Stencil passes then sweep the staged planes in place; the final per-cell pass gathers with
+// plain shared-memory indices, one wavefront per gather.  A back-trace that leaves the halo
+// (|v| >= 1 cell / iteration, never seen in the shipped saves) takes an exact, slow global-memory
+// path.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time)
+
 #include "wsb_cells.cuh"
 #include "wsb_ref_kernels.cuh"
 
@@ -36,26 +38,63 @@ constexpr int kTX = 64;   // tile width  (cells) — 2 warps wide, 1 KiB of floa
 constexpr int kTY = 16;   // tile height (cells)
 constexpr int kNT = 256;  // threads per CTA: thread (tx, ty0) computes rows ty0, ty0+4, ty0+8, ty0+12
 constexpr int kRowStep = kNT / kTX;
+// Every staged tile carries 4 extra columns on each side: the innermost TMA box coordinate must be
+// 16-byte aligned (4 floats), and the stencils need 2..3 of them anyway.
+constexpr int kHX = 4;
 
 // ---------------------------------------------------------------------------------------------
 // Tile staging
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ char4 as_char4(int w) { return *reinterpret_cast<const char4*>(&w); }
 // packed wall word (type | dist << 8 | vert << 16 | veg << 24)
 __device__ __forceinline__ bool wl_is_wall(int w) { return (w & 0xff00) == 0; }            // DISTANCE == 0
 __device__ __forceinline__ bool wl_is_land_wall(int w) { return (w & 0xffff) == 0x0001; }  // DISTANCE == 0 && TYPE == LAND
 
-// Stage the region [X0, X0+SW) x [Y0, Y0+SH) of AoS global arrays into per-channel shared-memory
-// planes THROUGH REGISTERS: load(ci, cil) returns the cell's registers (16-byte coalesced loads, 512 B
-// per warp), store(s, regs) scatters the channels with 4-byte stores.  G cells per thread are
-// loaded back to back before the first store, so G x 16..52 B per thread are in flight.
+// ---- TMA: one box per plane, completion through an mbarrier -----------------------------------
+template <int N>
+struct TileMaps { CUtensorMap m[N]; };  // passed as a __grid_constant__ kernel parameter
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// box with lower-left corner (x, y) of the plane described by `map` -> dense rows at `dst`;
+// coordinates outside the plane are filled with zeros
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_addr(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar))
+               : "memory");
+}
+// can this tile be staged by TMA?  rows must not wrap; columns must not wrap on a periodic domain
+// (a strip's out-of-range ghost-edge columns are zero-filled garbage nobody consumes)
+template <int SW, int SH>
+__device__ __forceinline__ bool tile_tma_ok(const Geom& g, int useTma, int X0, int Y0) {
+  return useTma && Y0 >= 0 && Y0 + SH <= g.H && (!g.wrap || (X0 >= 0 && X0 + SW <= g.pitch));
+}
+// shared-memory plane stride in floats: TMA destinations are 128-byte aligned
+template <int N> constexpr int plane_stride() { return (N + 31) / 32 * 32; }
+
+// Fallback: stage the region [X0, X0+SW) x [Y0, Y0+SH) THROUGH REGISTERS: load(ci, cil) returns
+// the cell's registers, store(s, regs) writes them to the shared-memory planes.  G cells per thread
+// are loaded back to back before the first store.
 //   s   shared-memory index of the cell
 //   ci  global cell index with the reference's periodic wrap (REPEAT textures)
 //   cil global cell index for the light texture (wrap S = REPEAT, wrap T = CLAMP_TO_EDGE, app.js:5276-5279)
-// Measured on B200 (profiles/): cp.async from the 16-byte-strided AoS source costs ~2x the LSU
-// data-pipe wavefronts of this path, and float planes make every later gather a single wavefront.
-// The wrap only exists on edge tiles (a block-uniform branch); interior tiles walk (row, column)
-// incrementally without divisions.
+// Interior tiles walk (row, column) incrementally without divisions.
 template <int SW, int SH, int G, class Load, class Store>
 __device__ __forceinline__ void stage_tile(const Geom& g, int X0, int Y0, Load load, Store store) {
   constexpr int N = SW * SH, R = (N + kNT - 1) / kNT;
@@ -93,7 +132,7 @@ __device__ __forceinline__ void stage_tile(const Geom& g, int X0, int Y0, Load l
   }
 }
 
-struct BaseWallRegs { float4 b; int w; };
+struct BaseWallRegs { float vx, vy, p, t; int w; };
 
 // ---------------------------------------------------------------------------------------------
 // Exact slow paths (global memory, any coordinates).  __noinline__ with pointer arguments so that
@@ -174,36 +213,54 @@ __device__ __forceinline__ bool tile_ok(int lx, int ly, int lo, int hi) {
 // k_fused_dry — pressure(prev) -> velocity -> advection(base): BASELINE config 2 / headline sweep
 // ---------------------------------------------------------------------------------------------
 constexpr int kHD = 2;                   // raw halo: advection +-1 of post-velocity, velocity +1, pressure -1
-constexpr int kSWD = kTX + 2 * kHD;      // 68
+constexpr int kSWD = kTX + 2 * kHX;      // 72
 constexpr int kSHD = kTY + 2 * kHD;      // 20
-constexpr int kND = kSWD * kSHD;         // 1360
-constexpr size_t kSmemDry = (size_t)kND * 4 * 6;  // float planes: VX, VY, P, T raw, T post-pressure, wall
+constexpr int kND = kSWD * kSHD;         // 1440
+constexpr int kPSD = plane_stride<kND>();  // 1440 floats
+constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;  // float planes: VX, VY, P, T raw, T post-pressure, wall; mbarrier
 
 // glob: base = base_1 (advection output, pressure pending), wall = wall_1.
+// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
 __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ GlobalCtx glob,
-                                                      const __grid_constant__ DevParams d, int applyPressure,
-                                                      float4* __restrict__ baseOut, unsigned* __restrict__ maxv) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                      const __grid_constant__ DevParams d,
+                                                      const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
+                                                      Planes4 baseOut, unsigned* __restrict__ maxv) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kND;
-  float* sP = sVY + kND;
-  float* sT = sP + kND;    // raw T
-  float* sT2 = sT + kND;   // T after the pressure pass
-  int* sWl = reinterpret_cast<int*>(sT2 + kND);
+  float* sVY = sVX + kPSD;
+  float* sP = sVY + kPSD;
+  float* sT = sP + kPSD;    // raw T
+  int* sWl = reinterpret_cast<int*>(sT + kPSD);
+  float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
   constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kHD, Y0 = blockIdx.y * kTY - kHD;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kHD;
 
-  stage_tile<kSWD, kSHD, 6>(
-      g, X0, Y0,
-      [&](int ci, int) { return BaseWallRegs{glob.base[ci], reinterpret_cast<const int*>(glob.wall)[ci]}; },
-      [&](int s, const BaseWallRegs& r) {
-        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
-        sWl[s] = r.w;
-      });
-  __syncthreads();
+  if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(mbar, 5u * kND * 4u);
+      tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
+      tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
+      tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
+      tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
+      tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
+    }
+    mbar_wait(mbar, 0);
+  } else {
+    stage_tile<kSWD, kSHD, 6>(
+        g, X0, Y0,
+        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], glob.wall[ci]}; },
+        [&](int s, const BaseWallRegs& r) {
+          sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
+          sWl[s] = r.w;
+        });
+    __syncthreads();
+  }
 
   // pressure pass of the previous iteration (pressureShader.frag); valid for i >= 1, j >= 1.
   // P' only reads velocities: in place.  T' reads the raw T below: separate plane.
@@ -227,12 +284,12 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
 
   // advection of the base field on the tile
   const int tx = tid % kTX, ty0 = tid / kTX;
-  const int x = X0 + kHD + tx;
+  const int x = X0 + kHX + tx;
   float vm = 0.0f;
   if (x < g.cx1) {
     const int gx = global_x(g, x);
     const float fragCoordX = (float)gx + 0.5f;
-    const int lxBase = tx + kHD;
+    const int lxBase = tx + kHX;
 #pragma unroll 1
     for (int ty = ty0; ty < kTY; ty += kRowStep) {
       const int y = Y0 + kHD + ty;
@@ -269,7 +326,7 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
       } else {  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
         base = make_float4(sVX[c], sVY[c], sP[c], ((w0 & 0xff) == WALLTYPE_LAND) ? 1000.0f : sT2[c]);
       }
-      baseOut[(size_t)y * g.pitch + x] = base;
+      baseOut.st((size_t)y * g.pitch + x, base);
     }
   }
   report_vmax(vm, maxv);
@@ -279,11 +336,12 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
 // k_fused_pvb — pressure(prev) -> velocity -> curl -> vorticity -> boundary
 // ---------------------------------------------------------------------------------------------
 constexpr int kH1 = 3;                      // halo of the pressure->boundary chain
-constexpr int kSW1 = kTX + 2 * kH1;         // 70
+constexpr int kSW1 = kTX + 2 * kHX;         // 72
 constexpr int kSH1 = kTY + 2 * kH1;         // 22
-constexpr int kN1 = kSW1 * kSH1;            // 1540 cells per staged tile
-// float planes: VX | VY | P | T raw, later curl | T post-pressure | wall | vortForce x | vortForce y
-constexpr size_t kSmem1 = (size_t)kN1 * 4 * 8;
+constexpr int kN1 = kSW1 * kSH1;            // 1584 cells per staged tile
+constexpr int kPS1 = plane_stride<kN1>();   // 1600 floats
+// float planes: VX | VY | P | T raw, later curl | wall | T post-pressure | vortForce x | vortForce y ; mbarrier
+constexpr size_t kSmem1 = (size_t)kPS1 * 4 * 8 + 16;
 
 // boundary_cell context positioned at shared-memory cell c: base / wall / vortForce from the tile,
 // own-cell water / light / feedback / deposition from registers (prefetched), the sparse
@@ -308,7 +366,7 @@ struct PvbAt {
   __device__ __forceinline__ float2 vort(int dx, int dy) const { return make_float2(sVFX[si(dx, dy)], sVFY[si(dx, dy)]); }
   __device__ __forceinline__ float4 water4(int dx, int dy) const {
     if (dx == 0 && dy == 0) return water0;
-    return glob.water[glob.idx_near(x + dx, y + dy)];
+    return glob.water.ld(glob.idx_near(x + dx, y + dy));
   }
   __device__ __forceinline__ float4 light4(int dx, int dy) const {
     if (dx == 0 && dy == 0) return make_float4(light0.x, light0.y, 0.0f, 0.0f);  // boundary reads SUNLIGHT, NET_HEATING only
@@ -319,33 +377,50 @@ struct PvbAt {
 };
 
 // glob: base = base_1, wall = wall_1, water = water_1, light = light_0 (glob.fb / glob.dep unused).
+// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSW1 x kSH1 box.
 // useFb: feedback / deposition hold data from the last particle pass; the kernel consumes them and
 // writes the zeros of the reference's gl.clear (app.js:5933-5934) back to the cells that were hit.
 __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
+                                                      const __grid_constant__ TileMaps<5> maps, int useTma,
                                                       const float* __restrict__ initial_T, int applyPressure, int useFb,
-                                                      float4* fb, float2* dep, float4* __restrict__ baseOut,
-                                                      float4* __restrict__ waterOut, char4* __restrict__ wallOut) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                      float4* fb, float2* dep, Planes4 baseOut, Planes4 waterOut,
+                                                      int* __restrict__ wallOut) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kN1;
-  float* sP = sVY + kN1;
-  float* sT = sP + kN1;      // raw T; dead after the pressure sweep ...
+  float* sVY = sVX + kPS1;
+  float* sP = sVY + kPS1;
+  float* sT = sP + kPS1;     // raw T; dead after the pressure sweep ...
   float* sCurl = sT;         // ... then curl
-  float* sT2 = sT + kN1;     // T after the pressure pass
-  int* sWl = reinterpret_cast<int*>(sT2 + kN1);
-  float* sVFX = reinterpret_cast<float*>(sWl + kN1);
-  float* sVFY = sVFX + kN1;
+  int* sWl = reinterpret_cast<int*>(sT + kPS1);
+  float* sT2 = reinterpret_cast<float*>(sWl + kPS1);     // T after the pressure pass
+  float* sVFX = sT2 + kPS1;
+  float* sVFY = sVFX + kPS1;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sVFY + kPS1);
   constexpr int SW = kSW1;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kH1, Y0 = blockIdx.y * kTY - kH1;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH1;
+  const bool viaTma = tile_tma_ok<kSW1, kSH1>(g, useTma, X0, Y0);
+
+  if (viaTma) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(mbar, 5u * kN1 * 4u);
+      tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
+      tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
+      tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
+      tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
+      tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
+    }
+  }
 
   // own-cell operands of the boundary pass: first row now (in flight during staging and the
   // sweeps below), the following rows one step ahead of their use
   const int tx = tid % kTX, ty0 = tid / kTX;
-  const int x = X0 + kH1 + tx;
+  const int x = X0 + kHX + tx;
   const bool colOk = x < g.cx1;
   float4 waterN = make_float4(0.f, 0.f, 0.f, 0.f), fbN = waterN;
   float2 lightN = make_float2(0.f, 0.f), depN = lightN;
@@ -353,8 +428,8 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
     const int y = Y0 + kH1 + ty;
     if (colOk && ty < kTY && y < g.H) {
       const int ci = y * g.pitch + x;
-      waterN = glob.water[ci];
-      lightN = *reinterpret_cast<const float2*>(glob.light + ci);
+      waterN = glob.water.ld(ci);
+      lightN = make_float2(glob.light.c[0][ci], glob.light.c[1][ci]);  // SUNLIGHT, NET_HEATING
       if (useFb) {
         fbN = fb[ci];
         depN = dep[ci];
@@ -363,14 +438,18 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
   };
   prefetch(ty0);
 
-  stage_tile<kSW1, kSH1, 4>(
-      g, X0, Y0,
-      [&](int ci, int) { return BaseWallRegs{glob.base[ci], reinterpret_cast<const int*>(glob.wall)[ci]}; },
-      [&](int s, const BaseWallRegs& r) {
-        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
-        sWl[s] = r.w;
-      });
-  __syncthreads();
+  if (viaTma) {
+    mbar_wait(mbar, 0);
+  } else {
+    stage_tile<kSW1, kSH1, 4>(
+        g, X0, Y0,
+        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], glob.wall[ci]}; },
+        [&](int s, const BaseWallRegs& r) {
+          sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
+          sWl[s] = r.w;
+        });
+    __syncthreads();
+  }
 
   // S1: pressure pass of the previous iteration; valid for i >= 1, j >= 1.  P' only reads
   // velocities: in place.  T' reads the raw T below: separate plane.
@@ -407,16 +486,16 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
 #pragma unroll 1
   for (int ty = ty0; ty < kTY; ty += kRowStep) {
     const int y = Y0 + kH1 + ty;
-    PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kH1, glob, x, y, waterN, fbN, lightN, depN};
+    PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kHX, glob, x, y, waterN, fbN, lightN, depN};
     prefetch(ty + kRowStep);
     if (colOk && y < g.H) {
       float4 b, w;
       char4 wl;
       boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
       const size_t ci = (size_t)y * g.pitch + x;
-      baseOut[ci] = b;
-      waterOut[ci] = w;
-      wallOut[ci] = wl;
+      baseOut.st(ci, b);
+      waterOut.st(ci, w);
+      wallOut[ci] = as_int(wl);
       if (useFb) {  // sprites are sparse: only cells that were hit cost a write
         if (c.fb0.x != 0.0f || c.fb0.y != 0.0f || c.fb0.z != 0.0f || c.fb0.w != 0.0f) fb[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c.dep0.x != 0.0f || c.dep0.y != 0.0f) dep[ci] = make_float2(0.f, 0.f);
@@ -429,11 +508,12 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
 // k_fused_adv — advection -> lighting
 // ---------------------------------------------------------------------------------------------
 constexpr int kH2 = 2;                  // halo: covers every back-trace with |v| < 1 and the sun-ray fetch
-constexpr int kSW2 = kTX + 2 * kH2;     // 68
+constexpr int kSW2 = kTX + 2 * kHX;     // 72
 constexpr int kSH2 = kTY + 2 * kH2;     // 20
-constexpr int kN2 = kSW2 * kSH2;        // 1360
-// float planes: VX VY P T | water total, cloud, precip, smoke | wall | light: sun, IR down, IR up
-constexpr size_t kSmem2 = (size_t)kN2 * 4 * 12;
+constexpr int kN2 = kSW2 * kSH2;        // 1440
+constexpr int kPS2 = plane_stride<kN2>();  // 1440 floats
+// float planes: VX VY P T | water total, cloud, precip, smoke | wall | light: sun, IR down, IR up ; mbarrier
+constexpr size_t kSmem2 = (size_t)kPS2 * 4 * 12 + 16;
 
 // light fetches of lighting_cell from the staged light planes (rows are staged with the
 // CLAMP_TO_EDGE rule, so the clamped row lighting_cell passes maps straight to a tile row)
@@ -446,55 +526,72 @@ struct TileLightCtx {
   __device__ __forceinline__ float lightIRup(int x, int y) const { return sLU[si(x, y)]; }
 };
 
-struct AdvRegs { float4 b, w, l; int wl; };
+struct AdvRegs { float4 b, w; float ls, ld, lu; int wl; };
 
 // glob: base_0, water_0, wall_0 (boundary output), light = light_src.
+// maps: TMA descriptors (kSW2 x kSH2 box) of base.c[0..3], water.c[0..3], wall, light.c[0], light.c[2], light.c[3].
 __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
+                                                      const __grid_constant__ TileMaps<12> maps, int useTma,
                                                       const float* __restrict__ initial_T, const float* __restrict__ sndT,
                                                       const float* __restrict__ sndW, const float* __restrict__ sndV,
-                                                      float4* __restrict__ baseOut, float4* __restrict__ waterOut,
-                                                      char4* __restrict__ wallOut, float4* __restrict__ lightOut,
-                                                      unsigned* __restrict__ maxv) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                      Planes4 baseOut, Planes4 waterOut, int* __restrict__ wallOut,
+                                                      Planes4 lightOut, unsigned* __restrict__ maxv) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kN2;
-  float* sP = sVY + kN2;
-  float* sT = sP + kN2;
-  float* sW0 = sT + kN2;
-  float* sW1 = sW0 + kN2;
-  float* sW2 = sW1 + kN2;
-  float* sW3 = sW2 + kN2;
-  int* sWl = reinterpret_cast<int*>(sW3 + kN2);
-  float* sLS = reinterpret_cast<float*>(sWl + kN2);
-  float* sLD = sLS + kN2;
-  float* sLU = sLD + kN2;
+  float* sVY = sVX + kPS2;
+  float* sP = sVY + kPS2;
+  float* sT = sP + kPS2;
+  float* sW0 = sT + kPS2;
+  float* sW1 = sW0 + kPS2;
+  float* sW2 = sW1 + kPS2;
+  float* sW3 = sW2 + kPS2;
+  int* sWl = reinterpret_cast<int*>(sW3 + kPS2);
+  float* sLS = reinterpret_cast<float*>(sWl + kPS2);
+  float* sLD = sLS + kPS2;
+  float* sLU = sLD + kPS2;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sLU + kPS2);
   constexpr int SW = kSW2;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kH2, Y0 = blockIdx.y * kTY - kH2;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH2;
 
-  stage_tile<kSW2, kSH2, 2>(
-      g, X0, Y0,
-      [&](int ci, int cil) { return AdvRegs{glob.base[ci], glob.water[ci], glob.light[cil], reinterpret_cast<const int*>(glob.wall)[ci]}; },
-      [&](int s, const AdvRegs& r) {
-        sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
-        sW0[s] = r.w.x; sW1[s] = r.w.y; sW2[s] = r.w.z; sW3[s] = r.w.w;
-        sWl[s] = r.wl;
-        sLS[s] = r.l.x; sLD[s] = r.l.z; sLU[s] = r.l.w;
-      });
-  __syncthreads();
+  // (interior rows never touch the CLAMP_TO_EDGE rule of the light texture, so one box shape serves all planes)
+  if (tile_tma_ok<kSW2, kSH2>(g, useTma, X0, Y0)) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(mbar, 12u * kN2 * 4u);
+      float* dst = sVX;
+#pragma unroll
+      for (int k = 0; k < 12; k++) tma_load_box(dst + k * kPS2, &maps.m[k], X0, Y0, mbar);
+    }
+    mbar_wait(mbar, 0);
+  } else {
+    stage_tile<kSW2, kSH2, 2>(
+        g, X0, Y0,
+        [&](int ci, int cil) {
+          return AdvRegs{glob.base.ld(ci), glob.water.ld(ci), glob.light.c[0][cil], glob.light.c[2][cil], glob.light.c[3][cil], glob.wall[ci]};
+        },
+        [&](int s, const AdvRegs& r) {
+          sVX[s] = r.b.x; sVY[s] = r.b.y; sP[s] = r.b.z; sT[s] = r.b.w;
+          sW0[s] = r.w.x; sW1[s] = r.w.y; sW2[s] = r.w.z; sW3[s] = r.w.w;
+          sWl[s] = r.wl;
+          sLS[s] = r.ls; sLD[s] = r.ld; sLU[s] = r.lu;
+        });
+    __syncthreads();
+  }
 
   const TileLightCtx lc{sLS, sLD, sLU, X0, Y0};
   const int tx = tid % kTX, ty0 = tid / kTX;
-  const int x = X0 + kH2 + tx;
+  const int x = X0 + kHX + tx;
   float vm = 0.0f;
   if (x < g.cx1) {
     const int gx = global_x(g, x);
     const float fragCoordX = (float)gx + 0.5f;
     const float texCoordX = fragCoordX * g.texelX;
-    const int lxBase = tx + kH2;
+    const int lxBase = tx + kHX;
 #pragma unroll 1
     for (int ty = ty0; ty < kTY; ty += kRowStep) {
       const int y = Y0 + kH2 + ty;
@@ -563,9 +660,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
         else wl = pack_wall(wType, wDist, wVert, wVeg);
       }
       const size_t ci = (size_t)y * g.pitch + x;
-      baseOut[ci] = base;
-      waterOut[ci] = water;
-      wallOut[ci] = wl;
+      baseOut.st(ci, base);
+      waterOut.st(ci, water);
+      wallOut[ci] = as_int(wl);
 
       // lighting needs base_1's temperature of the cell BELOW a water-surface air cell
       // (lightingShader.frag:105), i.e. that cell's advection result
@@ -586,7 +683,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
           TBelow = o.base.w;
         }
       }
-      lightOut[ci] = lighting_cell(lc, g, d, x, y, base.w, water, wl, TBelow);
+      lightOut.st(ci, lighting_cell(lc, g, d, x, y, base.w, water, wl, TBelow));
     }
   }
   report_vmax(vm, maxv);

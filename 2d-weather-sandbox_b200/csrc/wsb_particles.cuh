@@ -9,7 +9,7 @@
 // order; here the adds are L2 atomics (vector red.global.add.v4.f32 / v2.f32), so overlapping
 // sprites sum in arbitrary order — equal up to fp32 rounding of the sum.
 #pragma once
-#include "wsb_cells.cuh"
+#include "wsb_ref_kernels.cuh"
 
 namespace wsb {
 
@@ -26,9 +26,8 @@ __device__ __forceinline__ size_t nearest_texel(const Geom& g, float tx, float t
   return (size_t)iy * g.pitch + ix;
 }
 
-__device__ DropletResult droplet_update(const float* __restrict__ din, const float4* __restrict__ baseT,
-                                        const float4* __restrict__ waterT, const Geom& g, const DevParams& d,
-                                        float lightningStart, float inactiveDroplets) {
+__device__ DropletResult droplet_update(const float* __restrict__ din, const Planes4& baseT, const Planes4& waterT,
+                                        const Geom& g, const DevParams& d, float lightningStart, float inactiveDroplets) {
   const wsb_params& p = d.p;
   const float dropX = din[0], dropY = din[1], massW = din[2], massI = din[3], density = din[4];
   float newPosX = dropX, newPosY = dropY, newMassW = massW, newMassI = massI, newDensity = density;
@@ -44,8 +43,8 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const flo
     texCoordX = random2d(massW, dropX + iterNum * 0.3754f);
     texCoordY = random2d(massI, dropX + iterNum * 0.073162f);
     size_t ci = nearest_texel(g, texCoordX, texCoordY);
-    base = baseT[ci];
-    water = waterT[ci];
+    base = baseT.ld(ci);
+    water = waterT.ld(ci);
     realTemp = potentialToRealT(d, base.w, texCoordY);
     const float initalMass = 0.15f;
     float threshold = (realTemp > CtoK(0.0f)) ? p.aboveZeroThreshold : p.subZeroThreshold;
@@ -99,8 +98,8 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const flo
       texCoordX = dropX / 2.0f + 0.5f;
       texCoordY = dropY / 2.0f + 0.5f;
       size_t ci = nearest_texel(g, texCoordX, texCoordY);
-      water = waterT[ci];
-      base = baseT[ci];
+      water = waterT.ld(ci);
+      base = baseT.ld(ci);
       realTemp = potentialToRealT(d, base.w, texCoordY);
     }
     float totalMass = newMassW + newMassI;
@@ -110,7 +109,7 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const flo
       newMassW = -2.0f - dropX;
       newMassI = dropY;
     } else if (newPosY < -1.0f || water.x > 1000.0f) {  // :183
-      if (baseT[nearest_texel(g, texCoordX, texCoordY + g.texelY)].w > 500.0f) newPosY += g.texelY * 1.0f;
+      if (baseT.c[3][nearest_texel(g, texCoordX, texCoordY + g.texelY)] > 500.0f) newPosY += g.texelY * 1.0f;
       depR = newMassW;
       depS = newMassI;
       newMassW = -2.0f - dropX;
@@ -176,7 +175,7 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const flo
 // One thread per droplet.  Inactive droplets (the majority) only count themselves: the count is
 // reduced per block and lands on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
 __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__ dropsIn, float* __restrict__ dropsOut,
-                                                       const float4* __restrict__ baseT, const float4* __restrict__ waterT,
+                                                       Planes4 baseT, Planes4 waterT,
                                                        float4* __restrict__ fb, float2* __restrict__ dep,
                                                        const float* __restrict__ lightning,
                                                        const float* __restrict__ inactiveUniform, Geom g, DevParams d, int ND) {
