@@ -39,6 +39,7 @@ B_ALG = {
     "k_fused_adv": 100,  # R base 16 + water 16 + wall 4 + light (sun, IR down, IR up) 12; W base 16 + water 16 + wall 4 + light 16
     "k_fused_dry": 36,   # R base 16 + wall 4; W base 16
 }
+PREWARM_ITERS = 150      # untimed, before the W warm-up steps
 B_ALG_STEP_FULL = 104    # every live field read once + written once per iteration
 
 
@@ -252,9 +253,8 @@ def run_ours(args):
     # ---- device-timed leg: inputs resident in HBM -------------------------------------------
     # The GPU idles while the host generates the state; run until the SM clock has ramped up again
     # (untimed), then the W warm-up steps proper.
-    t_pre = time.perf_counter()
-    while not args.no_prewarm and time.perf_counter() - t_pre < 0.5:
-        sim.step(10)
+    if not args.no_prewarm:  # a FIXED count: every rank must run the same number of halo exchanges
+        sim.step(PREWARM_ITERS)
         sim.sync()
     sim.step(Wm)
     sim.sync()
@@ -309,7 +309,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"full physics {W}x{H} fp32 (pressure+velocity+vorticity+boundary+advection+condensation+lighting), no particles",
                        "grid": [W, H], "partition": f"{world} x-strip(s) of {lw} columns, ghost {gh}, one NCCL ring exchange per iteration" if world > 1 else "single GPU",
-                       "schedule": "fused: k_fused_pvb + k_fused_adv per iteration (TMA-staged channel planes)", "prewarm": "0.5 s of untimed iterations before the W warm-up steps (clock ramp-up)", "l2": "no flush: every plane is >= 256 MiB, far larger than the 126 MB L2",
+                       "schedule": "fused: k_fused_pvb + k_fused_adv per iteration (TMA-staged channel planes)", "prewarm": f"{PREWARM_ITERS} untimed iterations before the W warm-up steps (SM clock ramp-up after host-side state generation)", "l2": "no flush: every plane is >= 256 MiB, far larger than the 126 MB L2",
                        "max_abs_velocity_cells_per_iter": vmax, "state_finite": finite},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 
@@ -340,10 +340,8 @@ def dry_sweep_leg(W, H, K, Wm, peak, device_index):
     sim.upload(base, water, wall)
     del base, water, wall
     sim.set_profiling(True)
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < 0.5:  # clock ramp-up after the host-side state generation
-        sim.step_dry(20)
-        sim.sync()
+    sim.step_dry(4 * PREWARM_ITERS)  # clock ramp-up after the host-side state generation
+    sim.sync()
     sim.step_dry(Wm)
     sim.sync()
     sim.step_dry(K)
