@@ -172,8 +172,12 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const Pla
   return r;
 }
 
-// One thread per droplet.  Inactive droplets (the majority) only count themselves: the count is
-// reduced per block and lands on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
+// One thread per droplet for the update; the sprites are then rasterised WARP-COOPERATIVELY: each
+// lane that has a sprite broadcasts it in turn and all 32 lanes add one pixel each, walking the
+// sprite's rows — a 12-pixel row is 192 contiguous bytes of the feedback texture, so the vector
+// atomics of one instruction fall into a handful of sectors instead of 32 scattered ones.
+// Inactive droplets (the majority) only count themselves: the count is reduced per block and lands
+// on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
 __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__ dropsIn, float* __restrict__ dropsOut,
                                                        Planes4 baseT, Planes4 waterT,
                                                        float4* __restrict__ fb, float2* __restrict__ dep,
@@ -183,7 +187,12 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
   if (threadIdx.x == 0) sInactive = 0;
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   bool countsInactive = false;
+  // this lane's sprite: origin pixel, size (0 = none), payload
+  int xs = 0, ys = 0, sz = 0;
+  float4 sf = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 sd = make_float2(0.f, 0.f);
   if (n < ND) {
     DropletResult r = droplet_update(dropsIn + (size_t)n * 5, baseT, waterT, g, d, lightning[2], *inactiveUniform);
     float* o = dropsOut + (size_t)n * 5;
@@ -193,15 +202,29 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
     } else if (r.glX >= -1.0f && r.glX <= 1.0f && r.glY >= -1.0f && r.glY <= 1.0f) {
       const float xw = (r.glX + 1.0f) * 0.5f * g.Wf, yw = (r.glY + 1.0f) * 0.5f * g.Hf;
       const float half = r.pointSize * 0.5f;
-      const int xs = (int)ceilf(xw - half - 0.5f), ys = (int)ceilf(yw - half - 0.5f);
-      const int sz = (int)r.pointSize;
-      const bool hasDep = (r.deposition.x != 0.0f || r.deposition.y != 0.0f);
-      for (int j = max(ys, 0); j < min(ys + sz, g.H); j++)
-        for (int i = max(xs, 0); i < min(xs + sz, g.pitch); i++) {
-          size_t ci = (size_t)j * g.pitch + i;
-          atomicAdd(&fb[ci], r.feedback);
-          if (hasDep) atomicAdd(&dep[ci], r.deposition);
-        }
+      xs = (int)ceilf(xw - half - 0.5f);
+      ys = (int)ceilf(yw - half - 0.5f);
+      sz = (int)r.pointSize;
+      sf = r.feedback;
+      sd = r.deposition;
+    }
+  }
+  unsigned pending = __ballot_sync(0xffffffffu, sz > 0);
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const int bx = __shfl_sync(0xffffffffu, xs, src), by = __shfl_sync(0xffffffffu, ys, src), bs = __shfl_sync(0xffffffffu, sz, src);
+    const float4 f = make_float4(__shfl_sync(0xffffffffu, sf.x, src), __shfl_sync(0xffffffffu, sf.y, src),
+                                 __shfl_sync(0xffffffffu, sf.z, src), __shfl_sync(0xffffffffu, sf.w, src));
+    const float2 dp = make_float2(__shfl_sync(0xffffffffu, sd.x, src), __shfl_sync(0xffffffffu, sd.y, src));
+    const bool hasDep = (dp.x != 0.0f || dp.y != 0.0f);
+    for (int p = lane; p < bs * bs; p += 32) {
+      const int j = by + p / bs, i = bx + p % bs;
+      if (j >= 0 && j < g.H && i >= 0 && i < g.pitch) {
+        const size_t ci = (size_t)j * g.pitch + i;
+        atomicAdd(&fb[ci], f);
+        if (hasDep) atomicAdd(&dep[ci], dp);
+      }
     }
   }
   if (countsInactive) atomicAdd(&sInactive, 1);
