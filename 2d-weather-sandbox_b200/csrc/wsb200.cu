@@ -153,7 +153,7 @@ struct wsb_sim {
 
   // one RGBA32F texture = four float planes, with the TMA descriptors of each plane for the two
   // box shapes the fused kernels stage (tile + 2-cell halo: dry / advection; tile + 3: boundary)
-  struct Field { Planes4 p; CUtensorMap map2[4], map3[4]; };
+  struct Field { Planes4 p; CUtensorMap map2[4], map3[4], map0[4]; };  // map0: the bare tile (own-cell operands)
   Field base[2] = {}, water[2] = {}, light[2] = {};
   int* wall[2] = {};
   CUtensorMap wallMap2[2], wallMap3[2];
@@ -394,9 +394,14 @@ int fused_iteration(wsb_sim* s) {
   {
     ProfScope prof(s, WSB_KERNEL_PVB);
     GlobalCtx c = make_ctx(s, 1, 1, 1, 0);
-    TileMaps<5> maps;
-    for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].map3[k];
+    TileMaps<11> maps;
+    for (int k = 0; k < 4; k++) {
+      maps.m[k] = s->base[1].map3[k];
+      maps.m[5 + k] = s->water[1].map0[k];
+    }
     maps.m[4] = s->wallMap3[1];
+    maps.m[9] = s->light[0].map0[0];   // SUNLIGHT
+    maps.m[10] = s->light[0].map0[1];  // NET_HEATING
     auto launch_pvb = [&](int cx0, int cx1) {
       c.g.cx0 = cx0;
       c.g.cx1 = cx1;
@@ -498,7 +503,9 @@ int alloc_field(wsb_sim* s, wsb_sim::Field& f) {
   const size_t n = cells(s);
   for (int k = 0; k < 4; k++) {
     CK(cudaMalloc(&f.p.c[k], n * sizeof(float)));
-    if (s->use_tma && (make_map(s, &f.map2[k], f.p.c[k], false, kSW2, kSH2) || make_map(s, &f.map3[k], f.p.c[k], false, kSW1, kSH1))) return 1;
+    if (s->use_tma && (make_map(s, &f.map2[k], f.p.c[k], false, kSW2, kSH2) || make_map(s, &f.map3[k], f.p.c[k], false, kSW1, kSH1) ||
+                       make_map(s, &f.map0[k], f.p.c[k], false, kTX, kTY)))
+      return 1;
   }
   return 0;
 }

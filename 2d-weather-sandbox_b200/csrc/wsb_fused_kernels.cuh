@@ -340,8 +340,12 @@ constexpr int kSW1 = kTX + 2 * kHX;         // 72
 constexpr int kSH1 = kTY + 2 * kH1;         // 22
 constexpr int kN1 = kSW1 * kSH1;            // 1584 cells per staged tile
 constexpr int kPS1 = plane_stride<kN1>();   // 1600 floats
-// float planes: VX | VY | P | T raw, later curl | wall | T post-pressure | vortForce x | vortForce y ; mbarrier
-constexpr size_t kSmem1 = (size_t)kPS1 * 4 * 8 + 16;
+constexpr int kNVF = kSW1 * (kTY + 1);      // vortForce is only needed on the tile rows and the row below them
+constexpr int kPSV = plane_stride<kNVF>();  // 1248 floats
+constexpr int kNT0 = kTX * kTY;             // own-cell tiles (no halo): water x4, light sun + net heating
+// float planes: VX | VY | P | T raw, later curl | wall | T post-pressure | vortForce x | vortForce y |
+//               own-cell tiles: water total, cloud, precip, smoke, light sun, light net heating ; mbarrier
+constexpr size_t kSmem1 = (size_t)kPS1 * 4 * 6 + (size_t)kPSV * 4 * 2 + (size_t)kNT0 * 4 * 6 + 16;
 
 // boundary_cell context positioned at shared-memory cell c: base / wall / vortForce from the tile,
 // own-cell water / light / feedback / deposition from registers (prefetched), the sparse
@@ -352,8 +356,10 @@ struct PvbAt {
   int c;
   const GlobalCtx& glob;
   int x, y;
-  float4 water0, fb0;
-  float2 light0, dep0;
+  const float* sOwn;  // own-cell tiles [6][kNT0]: water x4, light sun, light net heating
+  int t;              // index of the cell in the own-cell tiles
+  float4 fb0;
+  float2 dep0;
   __device__ __forceinline__ int si(int dx, int dy) const { return c + dy * kSW1 + dx; }
   __device__ __forceinline__ float4 base4(int dx, int dy) const {
     const int s = si(dx, dy);
@@ -363,13 +369,17 @@ struct PvbAt {
   __device__ __forceinline__ float by(int dx, int dy) const { return sVY[si(dx, dy)]; }
   __device__ __forceinline__ float bt(int dx, int dy) const { return sT2[si(dx, dy)]; }
   __device__ __forceinline__ char4 wall4(int dx, int dy) const { return as_char4(sWl[si(dx, dy)]); }
-  __device__ __forceinline__ float2 vort(int dx, int dy) const { return make_float2(sVFX[si(dx, dy)], sVFY[si(dx, dy)]); }
+  // vortForce planes start at staged row kH1-1
+  __device__ __forceinline__ float2 vort(int dx, int dy) const {
+    const int s = si(dx, dy) - (kH1 - 1) * kSW1;
+    return make_float2(sVFX[s], sVFY[s]);
+  }
   __device__ __forceinline__ float4 water4(int dx, int dy) const {
-    if (dx == 0 && dy == 0) return water0;
+    if (dx == 0 && dy == 0) return make_float4(sOwn[t], sOwn[kNT0 + t], sOwn[2 * kNT0 + t], sOwn[3 * kNT0 + t]);
     return glob.water.ld(glob.idx_near(x + dx, y + dy));
   }
   __device__ __forceinline__ float4 light4(int dx, int dy) const {
-    if (dx == 0 && dy == 0) return make_float4(light0.x, light0.y, 0.0f, 0.0f);  // boundary reads SUNLIGHT, NET_HEATING only
+    if (dx == 0 && dy == 0) return make_float4(sOwn[4 * kNT0 + t], sOwn[5 * kNT0 + t], 0.0f, 0.0f);  // SUNLIGHT, NET_HEATING only
     return glob.light4(x + dx, y + dy);
   }
   __device__ __forceinline__ float4 fb4() const { return fb0; }
@@ -377,12 +387,13 @@ struct PvbAt {
 };
 
 // glob: base = base_1, wall = wall_1, water = water_1, light = light_0 (glob.fb / glob.dep unused).
-// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSW1 x kSH1 box.
+// maps: TMA descriptors — [0..4] base.c[0..3], wall with a kSW1 x kSH1 box; [5..10] water.c[0..3],
+// light.c[0], light.c[1] with a kTX x kTY box (the cell's own operands of the boundary pass).
 // useFb: feedback / deposition hold data from the last particle pass; the kernel consumes them and
 // writes the zeros of the reference's gl.clear (app.js:5933-5934) back to the cells that were hit.
-__global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
+__global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
-                                                      const __grid_constant__ TileMaps<5> maps, int useTma,
+                                                      const __grid_constant__ TileMaps<11> maps, int useTma,
                                                       const float* __restrict__ initial_T, int applyPressure, int useFb,
                                                       float4* fb, float2* dep, Planes4 baseOut, Planes4 waterOut,
                                                       int* __restrict__ wallOut) {
@@ -394,51 +405,32 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
   float* sCurl = sT;         // ... then curl
   int* sWl = reinterpret_cast<int*>(sT + kPS1);
   float* sT2 = reinterpret_cast<float*>(sWl + kPS1);     // T after the pressure pass
-  float* sVFX = sT2 + kPS1;
-  float* sVFY = sVFX + kPS1;
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sVFY + kPS1);
+  float* sVFX = sT2 + kPS1;  // staged rows kH1-1 .. kH1+kTY-1
+  float* sVFY = sVFX + kPSV;
+  float* sOwn = sVFY + kPSV;  // [6][kNT0]
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sOwn + 6 * kNT0);
   constexpr int SW = kSW1;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
   const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH1;
-  const bool viaTma = tile_tma_ok<kSW1, kSH1>(g, useTma, X0, Y0);
+  const int tx = tid % kTX, ty0 = tid / kTX;
+  const int x = X0 + kHX + tx;
+  const bool colOk = x < g.cx1;
 
-  if (viaTma) {
+  if (tile_tma_ok<kSW1, kSH1>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(mbar, 5u * kN1 * 4u);
+      mbar_expect_tx(mbar, 5u * kN1 * 4u + 6u * kNT0 * 4u);
       tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
       tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
       tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
       tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
       tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
+#pragma unroll
+      for (int k = 0; k < 6; k++) tma_load_box(sOwn + k * kNT0, &maps.m[5 + k], X0 + kHX, Y0 + kH1, mbar);
     }
-  }
-
-  // own-cell operands of the boundary pass: first row now (in flight during staging and the
-  // sweeps below), the following rows one step ahead of their use
-  const int tx = tid % kTX, ty0 = tid / kTX;
-  const int x = X0 + kHX + tx;
-  const bool colOk = x < g.cx1;
-  float4 waterN = make_float4(0.f, 0.f, 0.f, 0.f), fbN = waterN;
-  float2 lightN = make_float2(0.f, 0.f), depN = lightN;
-  auto prefetch = [&](int ty) {
-    const int y = Y0 + kH1 + ty;
-    if (colOk && ty < kTY && y < g.H) {
-      const int ci = y * g.pitch + x;
-      waterN = glob.water.ld(ci);
-      lightN = make_float2(glob.light.c[0][ci], glob.light.c[1][ci]);  // SUNLIGHT, NET_HEATING
-      if (useFb) {
-        fbN = fb[ci];
-        depN = dep[ci];
-      }
-    }
-  };
-  prefetch(ty0);
-
-  if (viaTma) {
     mbar_wait(mbar, 0);
   } else {
     stage_tile<kSW1, kSH1, 4>(
@@ -448,6 +440,15 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
           sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
           sWl[s] = r.w;
         });
+    for (int ty = ty0; ty < kTY; ty += kRowStep) {  // own-cell tiles
+      const int y = Y0 + kH1 + ty, t = ty * kTX + tx;
+      const bool ok = colOk && y < g.H;
+      const int ci = ok ? y * g.pitch + x : 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) sOwn[k * kNT0 + t] = ok ? glob.water.c[k][ci] : 0.0f;
+      sOwn[4 * kNT0 + t] = ok ? glob.light.c[0][ci] : 0.0f;
+      sOwn[5 * kNT0 + t] = ok ? glob.light.c[1][ci] : 0.0f;
+    }
     __syncthreads();
   }
 
@@ -477,8 +478,8 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
   // valid for 2 <= i <= SW-4
   for (int s = (kH1 - 1) * SW + tid; s < (kH1 + kTY) * SW; s += kNT) {
     const float2 vf = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - SW], sCurl[s + 1], sCurl[s + SW]);
-    sVFX[s] = vf.x;
-    sVFY[s] = vf.y;
+    sVFX[s - (kH1 - 1) * SW] = vf.x;
+    sVFY[s - (kH1 - 1) * SW] = vf.y;
   }
   __syncthreads();
 
@@ -486,13 +487,17 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_pvb(const __grid_constant__ Gl
 #pragma unroll 1
   for (int ty = ty0; ty < kTY; ty += kRowStep) {
     const int y = Y0 + kH1 + ty;
-    PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kHX, glob, x, y, waterN, fbN, lightN, depN};
-    prefetch(ty + kRowStep);
     if (colOk && y < g.H) {
+      const size_t ci = (size_t)y * g.pitch + x;
+      PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kHX, glob, x, y, sOwn, ty * kTX + tx,
+              make_float4(0.f, 0.f, 0.f, 0.f), make_float2(0.f, 0.f)};
+      if (useFb) {
+        c.fb0 = fb[ci];
+        c.dep0 = dep[ci];
+      }
       float4 b, w;
       char4 wl;
       boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
-      const size_t ci = (size_t)y * g.pitch + x;
       baseOut.st(ci, b);
       waterOut.st(ci, w);
       wallOut[ci] = as_int(wl);
