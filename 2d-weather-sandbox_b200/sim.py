@@ -168,6 +168,19 @@ class Simulation:
         sim._stations = sf.stations
         return sim
 
+    @classmethod
+    def new_simulation(cls, width: int, height: int, seed: float = 0.37, height_mult: float = 0.5,
+                       sim_height: float = 12000.0, **kw) -> "Simulation":
+        """'Create new simulation' (app.js:1357-1364 + setupShader.frag): default settings with the
+        chosen simulation height, terrain from `seed` / `height_mult`, all droplets inactive."""
+        from . import synth
+
+        g = P.resolve_settings(None, sim_height=sim_height)
+        base, water, wall, drops = synth.setup_state(width, height, seed, height_mult, g)
+        sim = cls(width, height, drops.shape[0], gui_controls=g, **kw)
+        sim.upload(base, water, wall, drops)
+        return sim
+
     def _check(self, rc: int):
         if rc != 0:
             raise WsbError(self.L.wsb_last_error().decode())

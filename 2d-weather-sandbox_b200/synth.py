@@ -175,6 +175,102 @@ def add_clouds(base, water, wall, n_blobs: int = 64, seed: int = 5, cloud_peak: 
         water[y0:y1, x0:x1, 0] += np.where(air, blob, 0).astype(np.float32)
 
 
+# --------------------------------------------------------------------------------------------
+# The reference's own new-simulation state: shaders/fragment/setupShader.frag:27-92, which app.js
+# renders into both framebuffers when no save file is loaded (app.js:5646-5657, 5729-5742).
+# --------------------------------------------------------------------------------------------
+def _f32(x):
+    return np.asarray(x, np.float32)
+
+
+def _setup_rand(n):
+    """setupShader.frag:27  rand(n) = fract(sin(n) * 43758.5453123).  Canonical form: sin evaluated
+    in double and rounded to fp32 (GPU sin of large arguments is implementation-defined), the rest
+    in fp32."""
+    n = _f32(n)
+    v = (np.sin(n.astype(np.float64)).astype(np.float32) * np.float32(43758.5453123)).astype(np.float32)
+    return (v - np.floor(v)).astype(np.float32)
+
+
+def _setup_noise(p):
+    """setupShader.frag:29-34"""
+    p = _f32(p)
+    fl = np.floor(p).astype(np.float32)
+    fc = (p - fl).astype(np.float32)
+    a, b = _setup_rand(fl), _setup_rand((fl + np.float32(1.0)).astype(np.float32))
+    mix = (a * (np.float32(1.0) - fc) + b * fc).astype(np.float32)
+    return (mix - np.float32(0.5)).astype(np.float32)
+
+
+def setup_state(w: int, h: int, seed: float = 0.37, height_mult: float = 0.5, g: dict | None = None,
+                with_droplets: bool = True, droplet_seed: int = 42):
+    """New-simulation initial state, restating setupShader.frag:36-92 in fp32: terrain from summed
+    value noise (all sea below heightMult 0.05, flat land below 0.10), land cells with 25 mm soil
+    moisture / vegetation / snow above 2000 m, water cells at 25 C, air at the initial temperature
+    profile with a dew point 2 K (lowest 20 %) or 20 K below the temperature.
+    `seed` and `height_mult` are the shader uniforms (mouse x / height in the reference).
+    Returns (base, water, wall, droplets)."""
+    g = g or P.resolve_settings(None)
+    f = np.float32
+    t0 = P.initial_T_profile(h, g)
+    lapse = f(P.dry_lapse(g))
+    sim_height = f(g["simHeight"])
+    texel_y = f(1.0 / h)
+    frag_x = (np.arange(w, dtype=np.float32) + f(0.5))
+    frag_y = (np.arange(h, dtype=np.float32) + f(0.5))
+    tex_y = (frag_y * texel_y).astype(np.float32)
+
+    height = np.zeros(w, np.float32)
+    height_m = np.zeros(w, np.float32)
+    hm = f(height_mult)
+    if hm < f(0.05):
+        pass  # all sea
+    elif hm < f(0.10):
+        height[:] = f(0.005)  # all land
+    else:
+        var = (frag_x * f(0.001)).astype(np.float32)
+        i = f(2.0)
+        while i < f(1000.0):  # :55-57
+            off = (_setup_rand((f(seed) + i).astype(np.float32)) * f(10.0)).astype(np.float32)
+            height = (height + _setup_noise((var * i + off).astype(np.float32)) * f(0.5) / i).astype(np.float32)
+            i = f(i * f(1.5))
+        height = (height * hm).astype(np.float32)
+        height_m = (height * sim_height).astype(np.float32)
+
+    base = np.zeros((h, w, 4), np.float32)
+    water = np.zeros((h, w, 4), np.float32)
+    wall32 = np.zeros((h, w, 4), np.int32)
+    is_wall = (tex_y[:, None] < texel_y) | (tex_y[:, None] < height[None, :])  # :63
+    sea = (height < texel_y)[None, :] & is_wall
+    land = is_wall & ~sea
+    # wall cells
+    wall32[..., 1] = np.where(is_wall, 0, 255)
+    wall32[..., 0] = np.where(sea, 2, np.where(land, 1, 0))
+    base[..., 3] = np.where(sea, f(25.0) + f(273.15), base[..., 3])
+    water[..., 2] = np.where(land, f(25.0), 0)
+    veg_noise = _setup_noise((frag_x * f(0.01) + _setup_rand(f(seed)) * f(10.0)).astype(np.float32))
+    veg = (f(110.0) - frag_y[:, None] * f(2.0) + veg_noise[None, :] * f(150.0)).astype(np.float32)
+    wall32[..., 3] = np.where(land, np.trunc(veg).astype(np.int32), 0)
+    mr = (f(0.0) + (height_m - f(2000.0)) * (f(100.0) - f(0.0)) / (f(5000.0) - f(2000.0))).astype(np.float32)  # map_range
+    snow = np.maximum(np.minimum(np.maximum(mr, f(0.0)), f(100.0)), f(0.0)).astype(np.float32)
+    water[..., 3] = np.where(land, snow[None, :], 0)
+    # air cells
+    air = ~is_wall
+    idx = (tex_y * (f(1.0) / texel_y)).astype(np.int32)
+    pot = t0[idx][:, None].astype(np.float32)
+    real = (pot - tex_y[:, None] * lapse).astype(np.float32)
+    spread = np.where(tex_y[:, None] < f(0.20), f(2.0), f(20.0)).astype(np.float32)
+    total = _max_water((real - spread).astype(np.float32))
+    cloud = np.maximum(total - _max_water(real), f(0.0)).astype(np.float32)
+    base[..., 3] = np.where(air, np.broadcast_to(pot, (h, w)), base[..., 3])
+    water[..., 0] = np.where(air, np.broadcast_to(total, (h, w)), 0)
+    water[..., 1] = np.where(air, np.broadcast_to(cloud, (h, w)), 0)
+    wall32[..., 2] = 100  # :91
+    wall = np.clip(wall32, -128, 127).astype(np.int8)  # RGBA8I store saturates
+    drops = init_rain_drops(num_droplets(w, h), droplet_seed) if with_droplets else None
+    return base, water, wall, drops
+
+
 def init_rain_drops(n: int, seed: int = 42) -> np.ndarray:
     """initRainDrops (app.js:4901-4913) with a seeded generator instead of Math.random():
     every droplet starts inactive (water mass in [-10,-9)) and the slots hold RNG seeds."""

@@ -423,3 +423,18 @@ def test_global_effects_and_sounding_forcing(schedule):
     assert not np.array_equal(idle.read_pixels(SIM.FIELD_BASE), sim.read_pixels(SIM.FIELD_BASE))
     sim.close()
     idle.close()
+
+
+def test_new_simulation_from_setup_state():
+    """'Create new simulation': setupShader-style state, default settings, 60 iterations of the
+    full loop (particles on) against the oracle."""
+    sim = wsb200.Simulation.new_simulation(192, 120, seed=0.61, height_mult=0.8)
+    g = sim.gui
+    base, water, wall, drops = wsb200.synth.setup_state(192, 120, 0.61, 0.8, g)
+    ora = make_oracle(g, base, water, wall, drops, fi=sim.frame_inputs)
+    assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), wall)
+    sim.step(60)
+    ora.step(60)
+    _assert_fields_equal(sim, ora, "new simulation", exact=False)
+    assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), ora.field(O.FIELD_WALL, 0))
+    sim.close()
