@@ -133,6 +133,25 @@ __global__ void k_unpack_halo(HaloPlanes hp, int pitch, int H, int lw, const int
   f[(size_t)y * pitch + kGhost + lw + i] = fromRight[t];
 }
 
+// n scattered texels of one RGBA32F field -> dense float4 array (weather-station style probes);
+// applyPressure: the field is the fused schedule's base_1 with the pressure pass still pending
+__global__ void k_gather_points(GlobalCtx c, Planes4 field, int applyPressure, int n, const int* __restrict__ xy, int lx_off,
+                                float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = xy[2 * i] + lx_off, y = xy[2 * i + 1];
+  if (x < 0 || x >= c.g.pitch || y < 0 || y >= c.g.H) {  // not in this rank's strip
+    out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float4 b = field.ld((size_t)y * c.g.pitch + x);
+  if (applyPressure) {
+    const char4 wYm = c.wall4(x, y - 1);
+    pressure_cell(b.x, b.y, b.z, b.w, c.bx(x - 1, y), c.by(x, y - 1), c.bt(x, y - 1), wYm.x, wYm.y);
+  }
+  out[i] = b;
+}
+
 // cuTensorMapEncodeTiled, resolved through the runtime (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -631,8 +650,10 @@ extern "C" {
 const char* wsb_last_error(void) { return g_err; }
 
 const char* wsb_build_info(void) {
-  return "libwsb200 abi " "1" " | sm_100a | nvcc " __VERSION__ " | fmad=false | tile "
-         "64x16, 256 threads, TMA-staged channel planes | ghost 8";
+#define WSB_STR2(x) #x
+#define WSB_STR(x) WSB_STR2(x)
+  return "libwsb200 abi 1 | sm_100a | nvcc " WSB_STR(__CUDACC_VER_MAJOR__) "." WSB_STR(__CUDACC_VER_MINOR__) "." WSB_STR(__CUDACC_VER_BUILD__)
+         " | fmad=false | tile 64x16, 256 threads, TMA-staged channel planes | ghost 8";
 }
 
 int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]) {
@@ -946,6 +967,40 @@ int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y,
     const char* sp = (const char*)src + ((size_t)y * s->pitch + lx0) * elt;
     CK(cudaMemcpy2DAsync(d, (size_t)w * elt, sp, (size_t)s->pitch * elt, (size_t)cw * elt, h, cudaMemcpyDeviceToHost, s->stream));
   }
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+int wsb_read_points(wsb_sim* s, int32_t field, int32_t view, int32_t n, const int32_t* xy, float* dst) {
+  if (!s || !xy || !dst) return fail("wsb_read_points: null argument");
+  if (n < 0) return fail("wsb_read_points: negative count");
+  if (view < WSB_VIEW_FRAMEBUFF_0 || view > WSB_VIEW_LATEST) return fail("wsb_read_points: unknown view %d", view);
+  if (n == 0) return 0;
+  if (use_device(s)) return 1;
+  for (int i = 0; i < n; i++)
+    if (xy[2 * i] < 0 || xy[2 * i] >= s->W || xy[2 * i + 1] < 0 || xy[2 * i + 1] >= s->H)
+      return fail("wsb_read_points: point %d (%d,%d) outside %dx%d", i, xy[2 * i], xy[2 * i + 1], s->W, s->H);
+  const bool fused = s->schedule == WSB_SCHEDULE_FUSED;
+  const int v1 = view == WSB_VIEW_FRAMEBUFF_1 ? 1 : 0;
+  const Planes4* planes = nullptr;
+  bool pressure = false;
+  switch (field) {
+    case WSB_FIELD_BASE:
+      if (fused) { planes = &s->base[1].p; pressure = (v1 == 0) && s->pressure_pending; }
+      else planes = &s->base[v1].p;
+      break;
+    case WSB_FIELD_WATER: planes = &s->water[v1].p; break;
+    case WSB_FIELD_LIGHT: planes = view == WSB_VIEW_LATEST ? &s->light[s->even ? 0 : 1].p : &s->light[v1].p; break;
+    default: return fail("wsb_read_points: field %d is not an RGBA32F simulation texture", field);
+  }
+  // scratch: [n float4 results][n int2 points]
+  if (need_scratch(s, (size_t)n + ((size_t)n * 8 + 15) / 16)) return 1;
+  int* dxy = reinterpret_cast<int*>(s->scratch + n);
+  CK(cudaMemcpyAsync(dxy, xy, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+  k_gather_points<<<(n + 127) / 128, 128, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), *planes, pressure ? 1 : 0, n, dxy,
+                                                          s->ghost - s->x_begin, s->scratch);
+  LAUNCHED("k_gather_points");
+  CK(cudaMemcpyAsync(dst, s->scratch, (size_t)n * 16, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }

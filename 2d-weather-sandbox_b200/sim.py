@@ -69,7 +69,7 @@ EXPORTS = [
     "wsb_comm_id_create", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
     "wsb_set_profiling", "wsb_kernel_time_ms", "wsb_set_params",
     "wsb_set_profiles", "wsb_set_frame_inputs", "wsb_step", "wsb_sync", "wsb_debug_run_pass",
-    "wsb_step_dry", "wsb_read_rect", "wsb_read_droplets", "wsb_get_inactive_droplets",
+    "wsb_step_dry", "wsb_read_rect", "wsb_read_points", "wsb_read_droplets", "wsb_get_inactive_droplets",
     "wsb_get_lightning", "wsb_get_iter", "wsb_set_iter", "wsb_get_strip", "wsb_get_max_velocity",
     "wsb_get_launch_count", "wsb_last_step_ms", "wsb_last_error", "wsb_build_info",
 ]
@@ -104,6 +104,7 @@ def load_library():
     L.wsb_debug_run_pass.argtypes = [vp, i32]
     L.wsb_step_dry.argtypes = [vp, i32]
     L.wsb_read_rect.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp]
+    L.wsb_read_points.argtypes = [vp, i32, i32, i32, vp, vp]
     L.wsb_read_droplets.argtypes = [vp, i32, i32, i32, vp]
     L.wsb_get_inactive_droplets.argtypes = [vp, f32p]
     L.wsb_get_lightning.argtypes = [vp, f32p]
@@ -321,6 +322,15 @@ class Simulation:
         elif out.shape != (h, w, ch) or out.dtype != dt or not out.flags.c_contiguous:
             raise WsbError("read_pixels: bad output array")
         self._check(self.L.wsb_read_rect(self.h, field, view, x, y, w, h, _ptr(out)))
+        return out
+
+    def read_points(self, field: int, points, view: int = VIEW_FRAMEBUFF_0) -> np.ndarray:
+        """Single texels of BASE / WATER / LIGHT at many (x, y) cells in one call (weather stations,
+        app.js:1082-1176).  Returns float32 [n][4]."""
+        pts = np.ascontiguousarray(points, np.int32).reshape(-1, 2)
+        out = np.zeros((pts.shape[0], 4), np.float32)
+        if pts.shape[0]:
+            self._check(self.L.wsb_read_points(self.h, field, view, pts.shape[0], _ptr(pts), _ptr(out)))
         return out
 
     def read_droplets(self, buffer: int = 2, first: int = 0, count: int | None = None) -> np.ndarray:

@@ -206,6 +206,12 @@ int wsb_step_dry(wsb_sim* sim, int32_t n_iters);
 int wsb_read_rect(wsb_sim* sim, int32_t field, int32_t view, int32_t x, int32_t y, int32_t w,
                   int32_t h, void* dst);
 
+/* Batched probes: n single texels of BASE / WATER / LIGHT at GLOBAL cell coordinates xy[n][2] in one
+ * call and one synchronisation (the reference issues one gl.readPixels per weather station and
+ * field every 208 iterations, app.js:1082-1176, 5997-6001 — each a pipeline stall).  dst is
+ * float[n][4]; on a strip, points outside the rank's columns return zeros. */
+int wsb_read_points(wsb_sim* sim, int32_t field, int32_t view, int32_t n, const int32_t* xy, float* dst);
+
 /* app.js:5017-5019, 5084-5086, 6595-6597. buffer: 0/1 = precipVertexBuffer_0/_1, 2 = the one
  * written last. */
 int wsb_read_droplets(wsb_sim* sim, int32_t buffer, int32_t first, int32_t count, float* dst);

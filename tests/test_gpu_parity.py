@@ -438,3 +438,20 @@ def test_new_simulation_from_setup_state():
     _assert_fields_equal(sim, ora, "new simulation", exact=False)
     assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), ora.field(O.FIELD_WALL, 0))
     sim.close()
+
+
+def test_read_points_matches_read_pixels(save100):
+    sim = wsb200.Simulation.from_save(save100)
+    sim.step(9)
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.integers(0, 100, 37), rng.integers(0, 100, 37)], 1)
+    for f, v in ((SIM.FIELD_BASE, SIM.VIEW_FRAMEBUFF_0), (SIM.FIELD_BASE, SIM.VIEW_FRAMEBUFF_1), (SIM.FIELD_WATER, SIM.VIEW_FRAMEBUFF_1),
+                 (SIM.FIELD_LIGHT, SIM.VIEW_LATEST)):
+        full = sim.read_pixels(f, view=v)
+        got = sim.read_points(f, pts, view=v)
+        assert np.array_equal(got, full[pts[:, 1], pts[:, 0]])
+    with pytest.raises(SIM.WsbError):
+        sim.read_points(SIM.FIELD_BASE, [[100, 0]])
+    with pytest.raises(SIM.WsbError):
+        sim.read_points(SIM.FIELD_WALL, [[1, 1]])
+    sim.close()
