@@ -16,11 +16,69 @@ Rows are bottom-up (GL origin); everything is little endian.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 import struct
 import zlib
 from dataclasses import dataclass, field
 
 import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CODEC = None
+
+
+def native_codec():
+    """libwsbsave.so (csrc/wsb_save.cpp): multi-threaded zlib codec, or None when it is not built
+    (the pure-Python zlib path below produces the same container, on one thread)."""
+    global _CODEC
+    if _CODEC is None:
+        path = os.path.join(_HERE, "csrc", "libwsbsave.so")
+        if not os.path.exists(path):
+            _CODEC = False
+        else:
+            L = ctypes.CDLL(path)
+            i64, vp = ctypes.c_int64, ctypes.c_void_p
+            L.wsb_save_compress_bound.restype = i64
+            L.wsb_save_compress_bound.argtypes = [i64]
+            L.wsb_save_compress.restype = i64
+            L.wsb_save_compress.argtypes = [vp, i64, vp, i64, ctypes.c_int32, ctypes.c_int32]
+            L.wsb_save_decompress.restype = i64
+            L.wsb_save_decompress.argtypes = [vp, i64, vp, i64]
+            L.wsb_save_inflated_size.restype = i64
+            L.wsb_save_inflated_size.argtypes = [vp, i64]
+            _CODEC = L
+    return _CODEC or None
+
+
+def deflate(payload: bytes, level: int = 6, threads: int = 0) -> bytes:
+    """zlib stream of `payload` (what pako.deflate produces in prepareDownload, app.js:6617)."""
+    L = native_codec()
+    if L is None:
+        return zlib.compress(payload, level)
+    src = np.frombuffer(payload, np.uint8)
+    cap = L.wsb_save_compress_bound(src.size)
+    out = np.empty(cap, np.uint8)
+    n = L.wsb_save_compress(src.ctypes.data, src.size, out.ctypes.data, cap, level, threads)
+    if n < 0:
+        raise RuntimeError(f"wsb_save_compress failed ({n})")
+    return out[:n].tobytes()
+
+
+def inflate(stream: bytes) -> bytes:
+    """pako.inflate (app.js:1267)."""
+    L = native_codec()
+    if L is None:
+        return zlib.decompress(stream)
+    src = np.frombuffer(stream, np.uint8)
+    n = L.wsb_save_inflated_size(src.ctypes.data, src.size)
+    if n < 0:
+        raise zlib.error(f"corrupt zlib stream ({n})")
+    out = np.empty(n, np.uint8)
+    m = L.wsb_save_decompress(src.ctypes.data, src.size, out.ctypes.data, n)
+    if m != n:
+        raise zlib.error(f"corrupt zlib stream ({m})")
+    return out.tobytes()
 
 SAVE_FILE_VERSION_ID = 263574036  # app.js:345
 LEGACY_VERSION_ID = 1939327491  # app.js:1265
@@ -56,7 +114,10 @@ def loads(blob: bytes) -> SaveFile:
     (version,) = struct.unpack_from("<I", blob, 0)
     if version not in (SAVE_FILE_VERSION_ID, LEGACY_VERSION_ID):
         raise IncompatibleFile(f"unknown save file version id {version}")
-    data = zlib.decompress(blob[4:])
+    try:
+        data = inflate(blob[4:])
+    except zlib.error as e:
+        raise IncompatibleFile(f"payload is not a zlib stream: {e}")
     w, h = struct.unpack_from("<HH", data, 0)
     n = w * h
     nd = num_droplets(w, h)
@@ -107,10 +168,10 @@ def payload(sf: SaveFile) -> bytes:
     return b"".join(parts)
 
 
-def dumps(sf: SaveFile, level: int = 6) -> bytes:
-    return struct.pack("<I", sf.version) + zlib.compress(payload(sf), level)
+def dumps(sf: SaveFile, level: int = 6, threads: int = 0) -> bytes:
+    return struct.pack("<I", sf.version) + deflate(payload(sf), level, threads)
 
 
-def save(path: str, sf: SaveFile, level: int = 6) -> None:
+def save(path: str, sf: SaveFile, level: int = 6, threads: int = 0) -> None:
     with open(path, "wb") as f:
-        f.write(dumps(sf, level))
+        f.write(dumps(sf, level, threads))

@@ -25,7 +25,7 @@ def built_library():
     """libwsb200.so, cross-compiled for sm_100a (nvcc works without a GPU)."""
     import wsb200
 
-    if not os.path.exists(wsb200.library_path()):
+    if not os.path.exists(wsb200.library_path()) or not os.path.exists(os.path.join(os.path.dirname(wsb200.library_path()), "libwsbsave.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "2d-weather-sandbox_b200", "csrc"), "-s"])
     return wsb200.library_path()
 

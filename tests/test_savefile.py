@@ -63,3 +63,28 @@ def test_ragged_droplet_count():
     assert back.width == 33 and back.height == 32
     assert np.array_equal(back.stations, [[3, 4]])
     assert back.settings_json == '{"a":1}'
+
+
+def test_native_codec_is_a_standard_zlib_stream(built_library):
+    """libwsbsave.so: chunked multi-threaded deflate stitched into one zlib stream."""
+    import time
+
+    L = S.native_codec()
+    assert L is not None, "libwsbsave.so not built (make -C 2d-weather-sandbox_b200/csrc)"
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 1000, (4 << 20) - 1, 4 << 20, (4 << 20) + 1, 13_000_000):
+        raw = (rng.integers(0, 8, n, dtype=np.uint8) * 17).tobytes()  # compressible, not trivial
+        for threads in (1, 4):
+            z = S.deflate(raw, 6, threads)
+            assert zlib.decompress(z) == raw          # any inflate (pako, zlib) reads it
+            assert S.inflate(z) == raw
+    # and the other direction: a stream written by plain zlib
+    raw = bytes(range(256)) * 5000
+    assert S.inflate(zlib.compress(raw, 9)) == raw
+    with pytest.raises(zlib.error):
+        S.inflate(b"\x78\x9c" + b"garbage-garbage-garbage")
+    # parallel deflate is faster than one thread on a field-sized buffer
+    big = np.sin(np.arange(6_000_000, dtype=np.float32)).tobytes()
+    t0 = time.perf_counter(); a = S.deflate(big, 6, 1); t1 = time.perf_counter(); b = S.deflate(big, 6, 4); t2 = time.perf_counter()
+    assert zlib.decompress(a) == big and zlib.decompress(b) == big
+    assert (t2 - t1) < (t1 - t0)
