@@ -704,6 +704,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
   g.texelX = (float)(1.0 / (double)s->W); g.texelY = (float)(1.0 / (double)s->H);   // app.js:5436 -> uniform2f
   g.Wf = (float)s->W; g.Hf = (float)s->H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;                                 // advectionShader.frag:69
+  g.cellHeightComp = 300.0f / g.Hf;                                                 // lightingShader.frag:44 (IEEE fp32 division, as on the device)
   memset(&s->dp, 0, sizeof(s->dp));
   s->dp.in.userInputType = -1;
   refresh_derived(s);

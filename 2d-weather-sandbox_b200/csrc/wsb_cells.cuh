@@ -20,6 +20,7 @@ struct Geom {
   float texelX, texelY;    // uniform texelSize: (float)(1.0/W), (float)(1.0/H)   app.js:5436
   float ltexelX, ltexelY;  // advectionShader.frag:69  vec2(1.)/resolution in fp32
   float Hf, Wf;
+  float cellHeightComp;    // lightingShader.frag:44  300. / resolution.y — uniform-only, divided once on the host
 };
 
 struct DevParams {
@@ -695,7 +696,7 @@ __device__ float4 lighting_cell(const C& c, const Geom& g, const DevParams& d, i
   const float fragCoordY = (float)y + 0.5f;
   if (fragCoordY >= g.Hf - 1.0f) return make_float4(d.in.sunIntensity, 0.0f, 0.0f, 0.0f);  // :40
   const float texCoordY = fragCoordY * g.texelY;
-  const float cellHeightCompensation = 300.0f / g.Hf;
+  const float cellHeightCompensation = g.cellHeightComp;  // 300.0f / g.Hf
   float sunlight;
   {  // :48-49, canonical fp32 bilinear in pixel space, wrap S = REPEAT, wrap T = CLAMP_TO_EDGE
     const int gx = global_x(g, x);

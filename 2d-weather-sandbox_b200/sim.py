@@ -61,7 +61,8 @@ class WsbError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "csrc", "libwsb200.so")
+    """csrc/libwsb200.so; WSB200_LIB overrides it (A/B timing of experimental builds)."""
+    return os.environ.get("WSB200_LIB") or os.path.join(_HERE, "csrc", "libwsb200.so")
 
 
 # every symbol include/wsb200.h declares (tests check the .so exports all of them)
