@@ -209,6 +209,50 @@ __device__ __forceinline__ bool tile_ok(int lx, int ly, int lo, int hi) {
   return (unsigned)(lx - lo) <= (unsigned)(SW - 2 - hi - lo) && (unsigned)(ly - lo) <= (unsigned)(SH - 2 - hi - lo);
 }
 
+// ---- stencil sweeps over the staged planes, two horizontally adjacent cells per thread -----------
+// (8-byte shared-memory accesses: half the load / store / loop instructions of a cell-per-thread
+// sweep; row strides and plane sizes are even, so an even index is 8-byte aligned)
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ int2 ld2(const int* p) { return *reinterpret_cast<const int2*>(p); }
+__device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+
+// pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
+// P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
+template <int SW, int N>
+__device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sVY, float* sP, const float* sT, float* sT2,
+                                               const int* sWl, int applyPressure) {
+  for (int s = SW + 2 * (int)threadIdx.x; s < N; s += 2 * kNT) {
+    float2 T = ld2(sT + s);
+    if (applyPressure) {
+      const int2 wb = ld2(sWl + s - SW);
+      const float2 Tb = ld2(sT + s - SW);
+      if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
+      if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
+      const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vyb = ld2(sVY + s - SW);
+      const float vxm = sVX[s - 1];
+      float2 P = ld2(sP + s);
+      P.x += (vxm - vx.x + vyb.x - vy.x) * 0.45f;
+      P.y += (vx.x - vx.y + vyb.y - vy.y) * 0.45f;
+      st2(sP + s, P);
+    }
+    st2(sT2 + s, T);
+  }
+}
+// velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
+template <int SW, int N>
+__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl) {
+  for (int s = SW + 2 * (int)threadIdx.x; s < N - SW; s += 2 * kNT) {
+    float2 vx = ld2(sVX + s), vy = ld2(sVY + s);
+    const float2 P = ld2(sP + s), Pu = ld2(sP + s + SW);
+    const float Pr = sP[s + 2];
+    const int2 w = ld2(sWl + s);
+    velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wl_is_wall(w.x) ? 0 : 1);
+    velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wl_is_wall(w.y) ? 0 : 1);
+    st2(sVX + s, vx);
+    st2(sVY + s, vy);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_fused_dry — pressure(prev) -> velocity -> advection(base): BASELINE config 2 / headline sweep
 // ---------------------------------------------------------------------------------------------
@@ -262,24 +306,9 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
     __syncthreads();
   }
 
-  // pressure pass of the previous iteration (pressureShader.frag); valid for i >= 1, j >= 1.
-  // P' only reads velocities: in place.  T' reads the raw T below: separate plane.
-  for (int s = SW + tid; s < kND; s += kNT) {
-    float T = sT[s];
-    if (applyPressure) {
-      if (wl_is_land_wall(sWl[s - SW])) T -= sT[s - SW] - 1000.0f;                       // pressureShader.frag:24-26
-      sP[s] += (sVX[s - 1] - sVX[s] + sVY[s - SW] - sVY[s]) * 0.45f;                    // :42
-    }
-    sT2[s] = T;
-  }
+  sweep_pressure<kSWD, kND>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
   __syncthreads();
-  // velocity (velocityShader.frag), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
-  for (int s = SW + tid; s < kND - SW; s += kNT) {
-    float vx = sVX[s], vy = sVY[s];
-    velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + SW], wl_is_wall(sWl[s]) ? 0 : 1);
-    sVX[s] = vx;
-    sVY[s] = vy;
-  }
+  sweep_velocity<kSWD, kND>(d, sVX, sVY, sP, sWl);
   __syncthreads();
 
   // advection of the base field on the tile
@@ -452,34 +481,26 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
     __syncthreads();
   }
 
-  // S1: pressure pass of the previous iteration; valid for i >= 1, j >= 1.  P' only reads
-  // velocities: in place.  T' reads the raw T below: separate plane.
-  for (int s = SW + tid; s < kN1; s += kNT) {
-    float T = sT[s];
-    if (applyPressure) {
-      if (wl_is_land_wall(sWl[s - SW])) T -= sT[s - SW] - 1000.0f;     // pressureShader.frag:24-26
-      sP[s] += (sVX[s - 1] - sVX[s] + sVY[s - SW] - sVY[s]) * 0.45f;  // :42
-    }
-    sT2[s] = T;
-  }
+  // S1 pressure (previous iteration), S2 velocity
+  sweep_pressure<kSW1, kN1>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
   __syncthreads();
-  // S2: velocity in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
-  for (int s = SW + tid; s < kN1 - SW; s += kNT) {
-    float vx = sVX[s], vy = sVY[s];
-    velocity_cell(d, vx, vy, sP[s], sP[s + 1], sP[s + SW], wl_is_wall(sWl[s]) ? 0 : 1);
-    sVX[s] = vx;
-    sVY[s] = vy;
-  }
+  sweep_velocity<kSW1, kN1>(d, sVX, sVY, sP, sWl);
   __syncthreads();
   // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
-  for (int s = SW + tid; s < kN1 - 2 * SW; s += kNT) sCurl[s] = curl_cell(sVX[s], sVY[s], sVX[s + SW], sVY[s + 1]);
+  for (int s = SW + 2 * tid; s < kN1 - 2 * SW; s += 2 * kNT) {
+    const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vxu = ld2(sVX + s + SW);
+    const float vyr = sVY[s + 2];
+    st2(sCurl + s, make_float2(curl_cell(vx.x, vy.x, vxu.x, vy.y), curl_cell(vx.y, vy.y, vxu.y, vyr)));
+  }
   __syncthreads();
   // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
   // valid for 2 <= i <= SW-4
-  for (int s = (kH1 - 1) * SW + tid; s < (kH1 + kTY) * SW; s += kNT) {
-    const float2 vf = vorticity_cell(sCurl[s], sCurl[s - 1], sCurl[s - SW], sCurl[s + 1], sCurl[s + SW]);
-    sVFX[s - (kH1 - 1) * SW] = vf.x;
-    sVFY[s - (kH1 - 1) * SW] = vf.y;
+  for (int s = (kH1 - 1) * SW + 2 * tid; s < (kH1 + kTY) * SW; s += 2 * kNT) {
+    const float2 c = ld2(sCurl + s), cd = ld2(sCurl + s - SW), cu = ld2(sCurl + s + SW);
+    const float cl = sCurl[s - 1], cr = sCurl[s + 2];
+    const float2 va = vorticity_cell(c.x, cl, cd.x, c.y, cu.x), vb = vorticity_cell(c.y, c.x, cd.y, cr, cu.y);
+    st2(sVFX + s - (kH1 - 1) * SW, make_float2(va.x, vb.x));
+    st2(sVFY + s - (kH1 - 1) * SW, make_float2(va.y, vb.y));
   }
   __syncthreads();
 

@@ -17,7 +17,8 @@ if mode in ("dry", "both"):
     sim = wsb200.Simulation(W, H, 0, gui_controls=g)
     sim.upload(*wsb200.synth.dry_state(W, H, seed=1234, g=g))
     sim.set_profiling(True)
-    sim.step_dry(5)
+    sim.step_dry(600)  # SM clock ramp-up after the host-side state generation
+    sim.sync()
     sim.step_dry(K)
     t, n = sim.kernel_time_ms(S.KERNEL_DRY)
     print(f"dry: {t / n:.4f} ms/launch  {36 * W * H / (t / n * 1e-3) / 1e9:.0f} GB/s  frac {36 * W * H / (t / n * 1e-3) / 1e9 / 6554.2:.3f}")
@@ -27,7 +28,8 @@ if mode in ("full", "both"):
     b, w, wl, _ = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=False)
     sim.upload(b, w, wl)
     sim.set_profiling(True)
-    sim.step(5)
+    sim.step(150)
+    sim.sync()
     sim.step(K)
     tp, n = sim.kernel_time_ms(S.KERNEL_PVB)
     ta, _ = sim.kernel_time_ms(S.KERNEL_ADV)
