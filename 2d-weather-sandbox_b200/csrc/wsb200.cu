@@ -486,8 +486,11 @@ int dry_iteration(wsb_sim* s) {
     // same canonical state as the full fused schedule: base_1 = advection output, pressure pending
     {
       ProfScope prof(s, WSB_KERNEL_DRY);
-      TileMaps<5> maps;
-      for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].map2[k];
+      TileMaps<9> maps;
+      for (int k = 0; k < 4; k++) {
+        maps.m[k] = s->base[1].map2[k];
+        maps.m[5 + k] = s->base[0].map0[k];  // result tiles (box stores)
+      }
       maps.m[4] = s->wallMap2[1];
       k_fused_dry<<<tile_grid(s), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0,
                                                                s->pressure_pending ? 1 : 0, s->base[0].p, s->maxv);
@@ -705,6 +708,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
   g.Wf = (float)s->W; g.Hf = (float)s->H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;                                 // advectionShader.frag:69
   g.cellHeightComp = 300.0f / g.Hf;                                                 // lightingShader.frag:44 (IEEE fp32 division, as on the device)
+  g.nearV = (g.Wg <= (1 << 19) && g.H <= (1 << 19)) ? 0.9f : -1.0f;                  // fp32 coordinate spacing <= 2^-5 (near_tap)
   memset(&s->dp, 0, sizeof(s->dp));
   s->dp.in.userInputType = -1;
   refresh_derived(s);

@@ -21,6 +21,7 @@ struct Geom {
   float ltexelX, ltexelY;  // advectionShader.frag:69  vec2(1.)/resolution in fp32
   float Hf, Wf;
   float cellHeightComp;    // lightingShader.frag:44  300. / resolution.y — uniform-only, divided once on the host
+  float nearV;             // fused kernels: |v| bound of the near back-trace (wsb_fused_kernels.cuh: near_tap); -1 = never
 };
 
 struct DevParams {

@@ -79,6 +79,30 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
                "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar))
                : "memory");
 }
+// dense rows at `src` -> box with lower-left corner (x, y) of the plane described by `map` (bulk
+// async group; elements outside the plane are clipped)
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, int x, int y, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+               "r"(smem_addr(src))
+               : "memory");
+}
+// generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// commit the issued stores and wait until shared memory has been read (the CTA may then exit)
+__device__ __forceinline__ void tma_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// compile-time switches of the round-2 optimisations (A/B timing: make EXTRA=-DWSB_OPT_...=0)
+#ifndef WSB_OPT_NEAR
+#define WSB_OPT_NEAR 1      // back-trace taps relative to the own cell when every |v| < 0.9
+#endif
+#ifndef WSB_OPT_TMAST
+#define WSB_OPT_TMAST 1     // results leave through shared-memory tiles and TMA box stores
+#endif
+#ifndef WSB_OPT_AIRFAST
+#define WSB_OPT_AIRFAST 1   // one test "all four texels are air" short-cuts the wall-aware bilerp weights
+#endif
 // can this tile be staged by TMA?  rows must not wrap; columns must not wrap on a periodic domain
 // (a strip's out-of-range ghost-edge columns are zero-filled garbage nobody consumes)
 template <int SW, int SH>
@@ -209,47 +233,94 @@ __device__ __forceinline__ bool tile_ok(int lx, int ly, int lo, int hi) {
   return (unsigned)(lx - lo) <= (unsigned)(SW - 2 - hi - lo) && (unsigned)(ly - lo) <= (unsigned)(SH - 2 - hi - lo);
 }
 
-// ---- stencil sweeps over the staged planes, two horizontally adjacent cells per thread -----------
-// (8-byte shared-memory accesses: half the load / store / loop instructions of a cell-per-thread
-// sweep; row strides and plane sizes are even, so an even index is 8-byte aligned)
+// Near back-trace.  With every velocity component of the cell below 0.9 cells / iteration and a
+// grid of at most 65536 x 65536 cells (fp32 spacing of the coordinates <= 2^-8), the sample
+// position minus one half lies in [cell - 1, cell + 1), so floor() is `cell - 1` or `cell` and one
+// comparison replaces the float->int conversions, the index arithmetic and the tile bounds test:
+// the tap is an OFFSET from the cell's own tile index.  fx, fy are the same fp32 subtractions
+// bilerp_setup performs, so the result is bit-identical to the general path.
+// The threshold travels as Geom::nearV (0.9, or -1 = never for grids beyond 2^19 cells a side).
+struct NearTap { bool left, down; float fx, fy; };
+__device__ __forceinline__ NearTap near_tap(float posx, float posy, float gxf, float gxm1, float gyf, float gym1) {
+  const float stx = posx - 0.5f, sty = posy - 0.5f;
+  NearTap n;
+  n.left = stx < gxf;
+  n.down = sty < gyf;
+  n.fx = stx - (n.left ? gxm1 : gxf);
+  n.fy = sty - (n.down ? gym1 : gyf);
+  return n;
+}
+// lower-left texel of the tap: `own` points at the cell's own entry, `below` one tile row lower
+template <class T>
+__device__ __forceinline__ const T* near_ptr(const NearTap& n, const T* own, const T* below) {
+  const T* q = n.down ? below : own;
+  return n.left ? q - 1 : q;
+}
+__device__ __forceinline__ float adv_vmax(const AdvVel& a) {
+  return fmaxf(fmaxf(fmaxf(fabsf(a.Vxx), fabsf(a.Vxy)), fmaxf(fabsf(a.Vyx), fabsf(a.Vyy))), fmaxf(fabsf(a.Px), fabsf(a.Py)));
+}
+// wall-aware bilerp weights (common.glsl:234-251) of the 2 x 2 footprint whose lower-left texel is
+// sWl[l]; the usual case — all four texels are air — is decided by one test on the DISTANCE bytes
+template <int SW>
+__device__ __forceinline__ WallMix tile_wall_mix(const int* sWl, int l, float fx, float fy) {
+  const unsigned char* wd = reinterpret_cast<const unsigned char*>(sWl + l) + 1;  // DISTANCE byte; 0 = wall
+  const unsigned a = wd[0], b = wd[4], c = wd[4 * SW], dd = wd[4 * SW + 4];
+  if (WSB_OPT_AIRFAST && min(min(a, b), min(c, dd)) != 0u) return WallMix{fx, fx, fy};
+  return wall_mix((int)a, (int)b, (int)c, (int)dd, fx, fy);
+}
+
+// ---- stencil sweeps over the staged planes, four horizontally adjacent cells per thread -----------
+// (16-byte shared-memory accesses: a quarter of the load / store / loop instructions of a
+// cell-per-thread sweep; row strides and plane sizes are multiples of 4 floats and planes are
+// 128-byte aligned, so an index that is a multiple of 4 is 16-byte aligned)
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ int2 ld2(const int* p) { return *reinterpret_cast<const int2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
 // P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
 template <int SW, int N>
 __device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sVY, float* sP, const float* sT, float* sT2,
                                                const int* sWl, int applyPressure) {
-  for (int s = SW + 2 * (int)threadIdx.x; s < N; s += 2 * kNT) {
-    float2 T = ld2(sT + s);
+  static_assert(SW % 4 == 0 && N % 4 == 0, "quad sweeps need rows of whole quads");
+  for (int s = SW + 4 * (int)threadIdx.x; s < N; s += 4 * kNT) {
+    float4 T = ld4(sT + s);
     if (applyPressure) {
-      const int2 wb = ld2(sWl + s - SW);
-      const float2 Tb = ld2(sT + s - SW);
+      const int4 wb = ld4(sWl + s - SW);
+      const float4 Tb = ld4(sT + s - SW);
       if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
       if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
-      const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vyb = ld2(sVY + s - SW);
+      if (wl_is_land_wall(wb.z)) T.z -= Tb.z - 1000.0f;
+      if (wl_is_land_wall(wb.w)) T.w -= Tb.w - 1000.0f;
+      const float4 vx = ld4(sVX + s), vy = ld4(sVY + s), vyb = ld4(sVY + s - SW);
       const float vxm = sVX[s - 1];
-      float2 P = ld2(sP + s);
+      float4 P = ld4(sP + s);
       P.x += (vxm - vx.x + vyb.x - vy.x) * 0.45f;
       P.y += (vx.x - vx.y + vyb.y - vy.y) * 0.45f;
-      st2(sP + s, P);
+      P.z += (vx.y - vx.z + vyb.z - vy.z) * 0.45f;
+      P.w += (vx.z - vx.w + vyb.w - vy.w) * 0.45f;
+      st4(sP + s, P);
     }
-    st2(sT2 + s, T);
+    st4(sT2 + s, T);
   }
 }
 // velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
 template <int SW, int N>
 __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl) {
-  for (int s = SW + 2 * (int)threadIdx.x; s < N - SW; s += 2 * kNT) {
-    float2 vx = ld2(sVX + s), vy = ld2(sVY + s);
-    const float2 P = ld2(sP + s), Pu = ld2(sP + s + SW);
-    const float Pr = sP[s + 2];
-    const int2 w = ld2(sWl + s);
+  for (int s = SW + 4 * (int)threadIdx.x; s < N - SW; s += 4 * kNT) {
+    float4 vx = ld4(sVX + s), vy = ld4(sVY + s);
+    const float4 P = ld4(sP + s), Pu = ld4(sP + s + SW);
+    const float Pr = sP[s + 4];
+    const int4 w = ld4(sWl + s);
     velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wl_is_wall(w.x) ? 0 : 1);
-    velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wl_is_wall(w.y) ? 0 : 1);
-    st2(sVX + s, vx);
-    st2(sVY + s, vy);
+    velocity_cell(d, vx.y, vy.y, P.y, P.z, Pu.y, wl_is_wall(w.y) ? 0 : 1);
+    velocity_cell(d, vx.z, vy.z, P.z, P.w, Pu.z, wl_is_wall(w.z) ? 0 : 1);
+    velocity_cell(d, vx.w, vy.w, P.w, Pr, Pu.w, wl_is_wall(w.w) ? 0 : 1);
+    st4(sVX + s, vx);
+    st4(sVY + s, vy);
   }
 }
 
@@ -261,13 +332,16 @@ constexpr int kSWD = kTX + 2 * kHX;      // 72
 constexpr int kSHD = kTY + 2 * kHD;      // 20
 constexpr int kND = kSWD * kSHD;         // 1440
 constexpr int kPSD = plane_stride<kND>();  // 1440 floats
-constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;  // float planes: VX, VY, P, T raw, T post-pressure, wall; mbarrier
+constexpr int kNT0 = kTX * kTY;          // cells of a tile without halo (own-cell operand tiles, result tiles)
+// float planes: VX, VY, P, T raw, wall, T post-pressure; result tiles x4; mbarrier
+constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + (size_t)kNT0 * 4 * 4 + 16;
 
 // glob: base = base_1 (advection output, pressure pending), wall = wall_1.
-// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
+// maps: [0..4] TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box (loads);
+//       [5..8] descriptors of baseOut.c[0..3] with a kTX x kTY box (stores).
 __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
-                                                      const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
+                                                      const __grid_constant__ TileMaps<9> maps, int useTma, int applyPressure,
                                                       Planes4 baseOut, unsigned* __restrict__ maxv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sVX = reinterpret_cast<float*>(smem_raw);
@@ -276,7 +350,8 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
   float* sT = sP + kPSD;    // raw T
   int* sWl = reinterpret_cast<int*>(sT + kPSD);
   float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
+  float* sOut = sT2 + kPSD;                            // [4][kNT0] result tiles
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sOut + 4 * kNT0);
   constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
@@ -314,17 +389,21 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
   // advection of the base field on the tile
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
+  // full tiles of a TMA-capable grid leave through shared memory and one box store per plane
+  const bool boxStore = WSB_OPT_TMAST && useTma && X0 + kHX + kTX <= g.cx1 && Y0 + kHD + kTY <= g.H;
   float vm = 0.0f;
   if (x < g.cx1) {
     const int gx = global_x(g, x);
-    const float fragCoordX = (float)gx + 0.5f;
+    const float gxf = (float)gx, gxm1 = gxf - 1.0f;
+    const float fragCoordX = gxf + 0.5f;
     const int lxBase = tx + kHX;
 #pragma unroll 1
     for (int ty = ty0; ty < kTY; ty += kRowStep) {
       const int y = Y0 + kHD + ty;
       if (y >= g.H) break;
       const int c = (ty + kHD) * SW + lxBase;
-      const float fragCoordY = (float)y + 0.5f;
+      const float gyf = (float)y;
+      const float fragCoordY = gyf + 0.5f;
       const int w0 = sWl[c];
       float4 base;
       if (!wl_is_wall(w0)) {
@@ -332,6 +411,30 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
         vm = fmaxf(vm, fmaxf(fabsf(vx00), fabsf(vy00)));
         const AdvVel a = adv_velocities(vx00, vy00, sVX[c - 1], sVY[c - SW], sVY[c + 1], sVX[c + SW], sVX[c + SW - 1],
                                         sVY[c - SW + 1]);
+#if WSB_OPT_NEAR
+        if (adv_vmax(a) < g.nearV) {  // taps are offsets from the own cell; no bounds test needed (halo 2)
+          const float gym1 = gyf - 1.0f;
+          const NearTap n1 = near_tap(fragCoordX - a.Vxx, fragCoordY - a.Vxy, gxf, gxm1, gyf, gym1);
+          const NearTap n2 = near_tap(fragCoordX - a.Vyx, fragCoordY - a.Vyy, gxf, gxm1, gyf, gym1);
+          const NearTap n3 = near_tap(fragCoordX - a.Px, fragCoordY - a.Py, gxf, gxm1, gyf, gym1);
+          // every plane is addressed off the VX plane's pointer: the plane displacement is an immediate
+          const float* pc = sVX + c;
+          const float* q1 = near_ptr(n1, pc, pc - SW);
+          const float* q2 = near_ptr(n2, pc, pc - SW) + kPSD;
+          const float* q3 = near_ptr(n3, pc, pc - SW);
+          base.x = mix2d(q1[0], q1[1], q1[SW], q1[SW + 1], n1.fx, n1.fx, n1.fy);
+          base.y = mix2d(q2[0], q2[1], q2[SW], q2[SW + 1], n2.fx, n2.fx, n2.fy);
+          const WallMix m = tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 4 * kPSD), 0, n3.fx, n3.fy);
+          const float* qP = q3 + 2 * kPSD;
+          const float* qT = q3 + 5 * kPSD;
+          base.z = mix2d(qP[0], qP[1], qP[SW], qP[SW + 1], m.ab, m.cd, m.abcd);
+          base.w = mix2d(qT[0], qT[1], qT[SW], qT[SW + 1], m.ab, m.cd, m.abcd);
+        } else {  // |v| >= 0.9 cells / iteration (never seen in the shipped saves): exact global-memory path
+          float vmSlow = 0.0f;  // a local of the cold branch: keeps vm itself in a register
+          base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
+          vm = fmaxf(vm, vmSlow);
+        }
+#else
         const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
         const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
         const BilerpSetup b3 = bilerp_setup(fragCoordX - a.Px, fragCoordY - a.Py);
@@ -343,19 +446,33 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
         if (tile_ok<kSWD, kSHD>(lx1, ly1, 1, 1) && tile_ok<kSWD, kSHD>(lx2, ly2, 1, 1) && tile_ok<kSWD, kSHD>(lx3, ly3, 1, 1)) {
           base.x = mix2d(sVX[l1], sVX[l1 + 1], sVX[l1 + SW], sVX[l1 + SW + 1], b1.fx, b1.fx, b1.fy);
           base.y = mix2d(sVY[l2], sVY[l2 + 1], sVY[l2 + SW], sVY[l2 + SW + 1], b2.fx, b2.fx, b2.fy);
-          const WallMix m = wall_mix(wl_is_wall(sWl[l3]) ? 0 : 1, wl_is_wall(sWl[l3 + 1]) ? 0 : 1, wl_is_wall(sWl[l3 + SW]) ? 0 : 1,
-                                     wl_is_wall(sWl[l3 + SW + 1]) ? 0 : 1, b3.fx, b3.fy);
+          const WallMix m = tile_wall_mix<SW>(sWl, l3, b3.fx, b3.fy);
           base.z = mix2d(sP[l3], sP[l3 + 1], sP[l3 + SW], sP[l3 + SW + 1], m.ab, m.cd, m.abcd);
           base.w = mix2d(sT2[l3], sT2[l3 + 1], sT2[l3 + SW], sT2[l3 + SW + 1], m.ab, m.cd, m.abcd);
         } else {
-          float vmSlow = 0.0f;  // a local of the cold branch: keeps vm itself in a register
+          float vmSlow = 0.0f;
           base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
           vm = fmaxf(vm, vmSlow);
         }
+#endif
       } else {  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
         base = make_float4(sVX[c], sVY[c], sP[c], ((w0 & 0xff) == WALLTYPE_LAND) ? 1000.0f : sT2[c]);
       }
-      baseOut.st((size_t)y * g.pitch + x, base);
+      if (boxStore) {
+        const int t = ty * kTX + tx;
+        sOut[t] = base.x; sOut[kNT0 + t] = base.y; sOut[2 * kNT0 + t] = base.z; sOut[3 * kNT0 + t] = base.w;
+      } else {
+        baseOut.st((size_t)y * g.pitch + x, base);
+      }
+    }
+  }
+  if (boxStore) {  // CTA-uniform
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) tma_store_box(&maps.m[5 + k], X0 + kHX, Y0 + kHD, sOut + k * kNT0);
+      tma_store_commit_wait();
     }
   }
   report_vmax(vm, maxv);
@@ -371,7 +488,6 @@ constexpr int kN1 = kSW1 * kSH1;            // 1584 cells per staged tile
 constexpr int kPS1 = plane_stride<kN1>();   // 1600 floats
 constexpr int kNVF = kSW1 * (kTY + 1);      // vortForce is only needed on the tile rows and the row below them
 constexpr int kPSV = plane_stride<kNVF>();  // 1248 floats
-constexpr int kNT0 = kTX * kTY;             // own-cell tiles (no halo): water x4, light sun + net heating
 // float planes: VX | VY | P | T raw, later curl | wall | T post-pressure | vortForce x | vortForce y |
 //               own-cell tiles: water total, cloud, precip, smoke, light sun, light net heating ; mbarrier
 constexpr size_t kSmem1 = (size_t)kPS1 * 4 * 6 + (size_t)kPSV * 4 * 2 + (size_t)kNT0 * 4 * 6 + 16;
@@ -487,20 +603,22 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   sweep_velocity<kSW1, kN1>(d, sVX, sVY, sP, sWl);
   __syncthreads();
   // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
-  for (int s = SW + 2 * tid; s < kN1 - 2 * SW; s += 2 * kNT) {
-    const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vxu = ld2(sVX + s + SW);
-    const float vyr = sVY[s + 2];
-    st2(sCurl + s, make_float2(curl_cell(vx.x, vy.x, vxu.x, vy.y), curl_cell(vx.y, vy.y, vxu.y, vyr)));
+  for (int s = SW + 4 * tid; s < kN1 - 2 * SW; s += 4 * kNT) {
+    const float4 vx = ld4(sVX + s), vy = ld4(sVY + s), vxu = ld4(sVX + s + SW);
+    const float vyr = sVY[s + 4];
+    st4(sCurl + s, make_float4(curl_cell(vx.x, vy.x, vxu.x, vy.y), curl_cell(vx.y, vy.y, vxu.y, vy.z),
+                               curl_cell(vx.z, vy.z, vxu.z, vy.w), curl_cell(vx.w, vy.w, vxu.w, vyr)));
   }
   __syncthreads();
   // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
   // valid for 2 <= i <= SW-4
-  for (int s = (kH1 - 1) * SW + 2 * tid; s < (kH1 + kTY) * SW; s += 2 * kNT) {
-    const float2 c = ld2(sCurl + s), cd = ld2(sCurl + s - SW), cu = ld2(sCurl + s + SW);
-    const float cl = sCurl[s - 1], cr = sCurl[s + 2];
-    const float2 va = vorticity_cell(c.x, cl, cd.x, c.y, cu.x), vb = vorticity_cell(c.y, c.x, cd.y, cr, cu.y);
-    st2(sVFX + s - (kH1 - 1) * SW, make_float2(va.x, vb.x));
-    st2(sVFY + s - (kH1 - 1) * SW, make_float2(va.y, vb.y));
+  for (int s = (kH1 - 1) * SW + 4 * tid; s < (kH1 + kTY) * SW; s += 4 * kNT) {
+    const float4 c = ld4(sCurl + s), cd = ld4(sCurl + s - SW), cu = ld4(sCurl + s + SW);
+    const float cl = sCurl[s - 1], cr = sCurl[s + 4];
+    const float2 v0 = vorticity_cell(c.x, cl, cd.x, c.y, cu.x), v1 = vorticity_cell(c.y, c.x, cd.y, c.z, cu.y),
+                 v2 = vorticity_cell(c.z, c.y, cd.z, c.w, cu.z), v3 = vorticity_cell(c.w, c.z, cd.w, cr, cu.w);
+    st4(sVFX + s - (kH1 - 1) * SW, make_float4(v0.x, v1.x, v2.x, v3.x));
+    st4(sVFY + s - (kH1 - 1) * SW, make_float4(v0.y, v1.y, v2.y, v3.y));
   }
   __syncthreads();
 
@@ -615,7 +733,8 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
   float vm = 0.0f;
   if (x < g.cx1) {
     const int gx = global_x(g, x);
-    const float fragCoordX = (float)gx + 0.5f;
+    const float gxf = (float)gx, gxm1 = gxf - 1.0f;
+    const float fragCoordX = gxf + 0.5f;
     const float texCoordX = fragCoordX * g.texelX;
     const int lxBase = tx + kHX;
 #pragma unroll 1
@@ -635,6 +754,40 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
         const float vx00 = sVX[c], vy00 = sVY[c];
         const AdvVel a = adv_velocities(vx00, vy00, sVX[c - 1], sVY[c - SW], sVY[c + 1], sVX[c + SW], sVX[c + SW - 1],
                                         sVY[c - SW + 1]);
+#if WSB_OPT_NEAR
+        if (adv_vmax(a) < g.nearV) {  // taps are offsets from the own cell; halo 2 covers them without a bounds test
+          const float gyf = (float)y, gym1 = gyf - 1.0f;
+          const float posPx = fragCoordX - a.Px, posPy = fragCoordY - a.Py;
+          const NearTap n1 = near_tap(fragCoordX - a.Vxx, fragCoordY - a.Vxy, gxf, gxm1, gyf, gym1);
+          const NearTap n2 = near_tap(fragCoordX - a.Vyx, fragCoordY - a.Vyy, gxf, gxm1, gyf, gym1);
+          const NearTap n3 = near_tap(posPx, posPy, gxf, gxm1, gyf, gym1);
+          const NearTap n4 = near_tap(posPx + 0.0f, posPy + 0.05f, gxf, gxm1, gyf, gym1);  // :137 precipitation falls
+          // every plane is addressed off the VX plane's pointer: the plane displacement is an immediate
+          const float* pc = sVX + c;
+          const float* q1 = near_ptr(n1, pc, pc - SW);
+          const float* q2 = near_ptr(n2, pc, pc - SW) + kPS2;
+          const float* q3 = near_ptr(n3, pc, pc - SW);
+          const float* q4 = near_ptr(n4, pc, pc - SW);
+          vm = fmaxf(vm, fmaxf(fabsf(vx00), fabsf(vy00)));
+          base.x = mix2d(q1[0], q1[1], q1[SW], q1[SW + 1], n1.fx, n1.fx, n1.fy);
+          base.y = mix2d(q2[0], q2[1], q2[SW], q2[SW + 1], n2.fx, n2.fx, n2.fy);
+          {
+            const WallMix m = tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 8 * kPS2), 0, n3.fx, n3.fy);
+            const float *qP = q3 + 2 * kPS2, *qT = q3 + 3 * kPS2, *qW0 = q3 + 4 * kPS2, *qW1 = q3 + 5 * kPS2, *qW3 = q3 + 7 * kPS2;
+            base.z = mix2d(qP[0], qP[1], qP[SW], qP[SW + 1], m.ab, m.cd, m.abcd);
+            base.w = mix2d(qT[0], qT[1], qT[SW], qT[SW + 1], m.ab, m.cd, m.abcd);
+            water.x = mix2d(qW0[0], qW0[1], qW0[SW], qW0[SW + 1], m.ab, m.cd, m.abcd);
+            water.y = mix2d(qW1[0], qW1[1], qW1[SW], qW1[SW + 1], m.ab, m.cd, m.abcd);
+            water.w = mix2d(qW3[0], qW3[1], qW3[SW], qW3[SW + 1], m.ab, m.cd, m.abcd);
+          }
+          {
+            const WallMix m = tile_wall_mix<SW>(reinterpret_cast<const int*>(q4 + 8 * kPS2), 0, n4.fx, n4.fy);
+            const float* qW2 = q4 + 6 * kPS2;
+            water.z = mix2d(qW2[0], qW2[1], qW2[SW], qW2[SW + 1], m.ab, m.cd, m.abcd);
+          }
+          adv_air_thermo(g, d, sndT, sndW, sndV, texCoordY, base, water);
+        } else {  // |v| >= 0.9 cells / iteration: exact global-memory path for the whole cell
+#else
         const BilerpSetup b1 = bilerp_setup(fragCoordX - a.Vxx, fragCoordY - a.Vxy);
         const BilerpSetup b2 = bilerp_setup(fragCoordX - a.Vyx, fragCoordY - a.Vyy);
         const float posPx = fragCoordX - a.Px, posPy = fragCoordY - a.Py;
@@ -651,8 +804,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
           base.x = mix2d(sVX[l1], sVX[l1 + 1], sVX[l1 + SW], sVX[l1 + SW + 1], b1.fx, b1.fx, b1.fy);
           base.y = mix2d(sVY[l2], sVY[l2 + 1], sVY[l2 + SW], sVY[l2 + SW + 1], b2.fx, b2.fx, b2.fy);
           {
-            const WallMix m = wall_mix(wl_is_wall(sWl[l3]) ? 0 : 1, wl_is_wall(sWl[l3 + 1]) ? 0 : 1, wl_is_wall(sWl[l3 + SW]) ? 0 : 1,
-                                       wl_is_wall(sWl[l3 + SW + 1]) ? 0 : 1, b3.fx, b3.fy);
+            const WallMix m = tile_wall_mix<SW>(sWl, l3, b3.fx, b3.fy);
             base.z = mix2d(sP[l3], sP[l3 + 1], sP[l3 + SW], sP[l3 + SW + 1], m.ab, m.cd, m.abcd);
             base.w = mix2d(sT[l3], sT[l3 + 1], sT[l3 + SW], sT[l3 + SW + 1], m.ab, m.cd, m.abcd);
             water.x = mix2d(sW0[l3], sW0[l3 + 1], sW0[l3 + SW], sW0[l3 + SW + 1], m.ab, m.cd, m.abcd);
@@ -660,12 +812,12 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
             water.w = mix2d(sW3[l3], sW3[l3 + 1], sW3[l3 + SW], sW3[l3 + SW + 1], m.ab, m.cd, m.abcd);
           }
           {
-            const WallMix m = wall_mix(wl_is_wall(sWl[l4]) ? 0 : 1, wl_is_wall(sWl[l4 + 1]) ? 0 : 1, wl_is_wall(sWl[l4 + SW]) ? 0 : 1,
-                                       wl_is_wall(sWl[l4 + SW + 1]) ? 0 : 1, b4.fx, b4.fy);
+            const WallMix m = tile_wall_mix<SW>(sWl, l4, b4.fx, b4.fy);
             water.z = mix2d(sW2[l4], sW2[l4 + 1], sW2[l4 + SW], sW2[l4 + SW + 1], m.ab, m.cd, m.abcd);
           }
           adv_air_thermo(g, d, sndT, sndW, sndV, texCoordY, base, water);
         } else {  // a back-trace left the halo: exact global-memory path for the whole cell
+#endif
           AdvSlowOut o;
           adv_cell_slow(&glob, &d, initial_T, sndT, sndW, sndV, x, y, &o);
           base = o.base;

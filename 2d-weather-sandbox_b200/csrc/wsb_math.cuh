@@ -40,7 +40,11 @@ enum { WALLTYPE_INERT = 0, WALLTYPE_LAND = 1, WALLTYPE_WATER = 2, WALLTYPE_FIRE 
 __device__ __forceinline__ float gmax(float a, float b) { return a < b ? b : a; }
 __device__ __forceinline__ float gmin(float a, float b) { return b < a ? b : a; }
 __device__ __forceinline__ float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+#ifdef WSB_EXP_FMAMIX  // timing experiment only (NOT the frozen semantics: results differ from the oracle)
+__device__ __forceinline__ float gmix(float a, float b, float t) { return __fmaf_rn(t, b, __fmaf_rn(-t, a, a)); }
+#else
 __device__ __forceinline__ float gmix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+#endif
 __device__ __forceinline__ float gfract(float x) { return x - floorf(x); }
 __device__ __forceinline__ float gmod(float x, float y) { return x - y * floorf(x / y); }
 __device__ __forceinline__ float glength(float x, float y) { return sqrtf(x * x + y * y); }
