@@ -172,10 +172,10 @@ struct wsb_sim {
 
   // one RGBA32F texture = four float planes, with the TMA descriptors of each plane for the two
   // box shapes the fused kernels stage (tile + 2-cell halo: dry / advection; tile + 3: boundary)
-  struct Field { Planes4 p; CUtensorMap map2[4], map3[4], map0[4]; };  // map0: the bare tile (own-cell operands)
+  struct Field { Planes4 p; CUtensorMap map2[4], map3[4], map0[4], mapD[4]; };  // map0: the bare tile (own-cell operands); mapD: dry-sweep box
   Field base[2] = {}, water[2] = {}, light[2] = {};
   int* wall[2] = {};
-  CUtensorMap wallMap2[2], wallMap3[2];
+  CUtensorMap wallMap2[2], wallMap3[2], wallMapD[2];
   bool use_tma = false;
   float4* fb = nullptr;
   float2 *dep = nullptr, *vort = nullptr;
@@ -486,13 +486,10 @@ int dry_iteration(wsb_sim* s) {
     // same canonical state as the full fused schedule: base_1 = advection output, pressure pending
     {
       ProfScope prof(s, WSB_KERNEL_DRY);
-      TileMaps<9> maps;
-      for (int k = 0; k < 4; k++) {
-        maps.m[k] = s->base[1].map2[k];
-        maps.m[5 + k] = s->base[0].map0[k];  // result tiles (box stores)
-      }
-      maps.m[4] = s->wallMap2[1];
-      k_fused_dry<<<tile_grid(s), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0,
+      TileMaps<5> maps;
+      for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].mapD[k];
+      maps.m[4] = s->wallMapD[1];
+      k_fused_dry<<<dim3((s->pitch + kTX - 1) / kTX, (s->H + kTYD - 1) / kTYD), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0,
                                                                s->pressure_pending ? 1 : 0, s->base[0].p, s->maxv);
       LAUNCHED("k_fused_dry");
     }
@@ -526,7 +523,7 @@ int alloc_field(wsb_sim* s, wsb_sim::Field& f) {
   for (int k = 0; k < 4; k++) {
     CK(cudaMalloc(&f.p.c[k], n * sizeof(float)));
     if (s->use_tma && (make_map(s, &f.map2[k], f.p.c[k], false, kSW2, kSH2) || make_map(s, &f.map3[k], f.p.c[k], false, kSW1, kSH1) ||
-                       make_map(s, &f.map0[k], f.p.c[k], false, kTX, kTY)))
+                       make_map(s, &f.map0[k], f.p.c[k], false, kTX, kTY) || make_map(s, &f.mapD[k], f.p.c[k], false, kSWD, kSHD)))
       return 1;
   }
   return 0;
@@ -536,7 +533,7 @@ int alloc_all(wsb_sim* s) {
   const size_t n = cells(s);
   // TMA needs 16-byte row strides and at least one box per dimension; anything else is staged through registers
   s->use_tma = false;
-  if (s->pitch % 4 == 0 && s->pitch >= kSW1 && s->H >= kSH1) {
+  if (s->pitch % 4 == 0 && s->pitch >= kSW1 && s->H >= (kSH1 > kSHD ? kSH1 : kSHD)) {
     if (!g_encode) {
       void* fn = nullptr;
       cudaDriverEntryPointQueryResult q;
@@ -549,7 +546,9 @@ int alloc_all(wsb_sim* s) {
   for (int k = 0; k < 2; k++) {
     if (alloc_field(s, s->base[k]) || alloc_field(s, s->water[k]) || alloc_field(s, s->light[k])) return 1;
     CK(cudaMalloc(&s->wall[k], n * sizeof(int)));
-    if (s->use_tma && (make_map(s, &s->wallMap2[k], s->wall[k], true, kSW2, kSH2) || make_map(s, &s->wallMap3[k], s->wall[k], true, kSW1, kSH1))) return 1;
+    if (s->use_tma && (make_map(s, &s->wallMap2[k], s->wall[k], true, kSW2, kSH2) || make_map(s, &s->wallMap3[k], s->wall[k], true, kSW1, kSH1) ||
+                       make_map(s, &s->wallMapD[k], s->wall[k], true, kSWD, kSHD)))
+      return 1;
     if (s->ND) CK(cudaMalloc(&s->drops[k], (size_t)s->ND * 5 * sizeof(float)));
   }
   CK(cudaMalloc(&s->fb, n * sizeof(float4)));

@@ -52,12 +52,34 @@ __device__ __forceinline__ float potentialToRealT(const DevParams& d, float pot,
   return pot - texCoordY * d.p.dryLapse;  // common.glsl:151-153
 }
 
-// largest |v| component seen by advection: warp-reduce (non-negative floats order like their bit
-// patterns), one atomic per warp.  Safe with partially active warps.
+// Largest |v| component seen by advection since the upload — a RUNNING maximum, so the global
+// atomic is only issued by whoever holds something larger than the current value (one L2 read
+// otherwise).  Measured (profiles/r2_vmax_atomics.md): an unconditional same-address atomicMax per
+// warp — 524 288 per launch at 16384 x 4096 — runs at ~0.43 atomics/ns and, depending on which L2
+// slice the word lands in, set the whole kernel's duration (1.22 ms instead of 0.63 ms).
+// Non-negative floats order like their bit patterns.  Safe with partially active warps.
 __device__ __forceinline__ void report_vmax(float vm, unsigned* __restrict__ maxv) {
+#ifdef WSB_EXP_NO_VMAX  // timing experiment only
+  return;
+#endif
   const unsigned m = __activemask();
   const unsigned r = __reduce_max_sync(m, __float_as_uint(vm));
-  if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == (unsigned)(__ffs(m) - 1) && r != 0u) atomicMax(maxv, r);
+  if ((threadIdx.x + threadIdx.y * blockDim.x) % 32 == (unsigned)(__ffs(m) - 1) && r > __ldcg(maxv)) atomicMax(maxv, r);
+}
+// CTA-wide variant for the fused kernels: warps combine in shared memory (`sMax`, zeroed by the
+// caller before an earlier __syncthreads), thread 0 talks to global memory.  Every thread of the
+// CTA must call it.
+__device__ __forceinline__ void report_vmax_cta(float vm, unsigned* __restrict__ maxv, unsigned* sMax) {
+#ifdef WSB_EXP_NO_VMAX
+  return;
+#endif
+  const unsigned r = __reduce_max_sync(0xffffffffu, __float_as_uint(vm));
+  if ((threadIdx.x & 31) == 0 && r != 0u) atomicMax(sMax, r);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned v = *sMax;
+    if (v > __ldcg(maxv)) atomicMax(maxv, v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

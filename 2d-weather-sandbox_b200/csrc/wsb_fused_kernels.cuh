@@ -79,26 +79,9 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
                "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar))
                : "memory");
 }
-// dense rows at `src` -> box with lower-left corner (x, y) of the plane described by `map` (bulk
-// async group; elements outside the plane are clipped)
-__device__ __forceinline__ void tma_store_box(const CUtensorMap* map, int x, int y, const void* src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
-               "r"(smem_addr(src))
-               : "memory");
-}
-// generic-proxy writes to shared memory (st.shared) -> visible to the async proxy (TMA store)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// commit the issued stores and wait until shared memory has been read (the CTA may then exit)
-__device__ __forceinline__ void tma_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-// compile-time switches of the round-2 optimisations (A/B timing: make EXTRA=-DWSB_OPT_...=0)
+// compile-time switches for A/B timing (make variant OUT=... EXTRA="-DWSB_OPT_NEAR=0 ...", profiles/tools/)
 #ifndef WSB_OPT_NEAR
 #define WSB_OPT_NEAR 1      // back-trace taps relative to the own cell when every |v| < 0.9
-#endif
-#ifndef WSB_OPT_TMAST
-#define WSB_OPT_TMAST 1     // results leave through shared-memory tiles and TMA box stores
 #endif
 #ifndef WSB_OPT_AIRFAST
 #define WSB_OPT_AIRFAST 1   // one test "all four texels are air" short-cuts the wall-aware bilerp weights
@@ -269,10 +252,16 @@ __device__ __forceinline__ WallMix tile_wall_mix(const int* sWl, int l, float fx
   return wall_mix((int)a, (int)b, (int)c, (int)dd, fx, fy);
 }
 
-// ---- stencil sweeps over the staged planes, four horizontally adjacent cells per thread -----------
-// (16-byte shared-memory accesses: a quarter of the load / store / loop instructions of a
-// cell-per-thread sweep; row strides and plane sizes are multiples of 4 floats and planes are
-// 128-byte aligned, so an index that is a multiple of 4 is 16-byte aligned)
+// ---- stencil sweeps over the staged planes ------------------------------------------------------
+// Two variants, same arithmetic: PAIR (two horizontally adjacent cells per thread, 8-byte accesses)
+// and QUAD (four cells, 16-byte accesses).  QUAD executes ~25 % fewer instructions, but the sweeps
+// are bound by shared-memory wavefronts and by how many warps have work between two barriers, not
+// by issue slots: measured on the dry sweep (profiles/r2_dry_variants.md) PAIR is 7 % faster, so it
+// is the default.  Row strides and plane sizes are multiples of 4 floats and planes are 128-byte
+// aligned, so an even index is 8-byte and a multiple of 4 is 16-byte aligned.
+#ifndef WSB_SWEEP_QUAD
+#define WSB_SWEEP_QUAD 0
+#endif
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ int2 ld2(const int* p) { return *reinterpret_cast<const int2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
@@ -280,6 +269,7 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+#if WSB_SWEEP_QUAD
 // pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
 // P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
 template <int SW, int N>
@@ -324,24 +314,80 @@ __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, f
   }
 }
 
+#else
+// pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
+// P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
+template <int SW, int N>
+__device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sVY, float* sP, const float* sT, float* sT2,
+                                               const int* sWl, int applyPressure) {
+  for (int s = SW + 2 * (int)threadIdx.x; s < N; s += 2 * kNT) {
+    float2 T = ld2(sT + s);
+    if (applyPressure) {
+      const int2 wb = ld2(sWl + s - SW);
+      const float2 Tb = ld2(sT + s - SW);
+      if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
+      if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
+      const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vyb = ld2(sVY + s - SW);
+      const float vxm = sVX[s - 1];
+      float2 P = ld2(sP + s);
+      P.x += (vxm - vx.x + vyb.x - vy.x) * 0.45f;
+      P.y += (vx.x - vx.y + vyb.y - vy.y) * 0.45f;
+      st2(sP + s, P);
+    }
+    st2(sT2 + s, T);
+  }
+}
+// velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
+template <int SW, int N>
+__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl) {
+  for (int s = SW + 2 * (int)threadIdx.x; s < N - SW; s += 2 * kNT) {
+    float2 vx = ld2(sVX + s), vy = ld2(sVY + s);
+    const float2 P = ld2(sP + s), Pu = ld2(sP + s + SW);
+    const float Pr = sP[s + 2];
+    const int2 w = ld2(sWl + s);
+    velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wl_is_wall(w.x) ? 0 : 1);
+    velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wl_is_wall(w.y) ? 0 : 1);
+    st2(sVX + s, vx);
+    st2(sVY + s, vy);
+  }
+}
+
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // k_fused_dry — pressure(prev) -> velocity -> advection(base): BASELINE config 2 / headline sweep
 // ---------------------------------------------------------------------------------------------
 constexpr int kHD = 2;                   // raw halo: advection +-1 of post-velocity, velocity +1, pressure -1
 constexpr int kSWD = kTX + 2 * kHX;      // 72
-constexpr int kSHD = kTY + 2 * kHD;      // 20
-constexpr int kND = kSWD * kSHD;         // 1440
-constexpr int kPSD = plane_stride<kND>();  // 1440 floats
-constexpr int kNT0 = kTX * kTY;          // cells of a tile without halo (own-cell operand tiles, result tiles)
-// float planes: VX, VY, P, T raw, wall, T post-pressure; result tiles x4; mbarrier
-constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + (size_t)kNT0 * 4 * 4 + 16;
+// Tile height of the dry sweep.  A taller tile amortises the halo rows the sweeps recompute and the
+// TMA fill (staged / computed cells: 1.41 at 16 rows, 1.29 at 28) until shared memory costs a
+// resident CTA: measured 0.620 ms (16) / 0.585 (20) / 0.560 (24) / 0.547 (28) / 0.576 (32, 3 CTAs) /
+// 0.658 (48, 2 CTAs) per launch at 16384 x 4096 (profiles/r2_dry_variants.md).  28 rows = 55.3 KB,
+// the tallest tile that still fits 4 CTAs per SM.
+#ifndef WSB_DRY_TY
+#define WSB_DRY_TY 28
+#endif
+constexpr int kTYD = WSB_DRY_TY;
+constexpr int kSHD = kTYD + 2 * kHD;     // 32
+constexpr int kND = kSWD * kSHD;         // 2304
+constexpr int kPSD = plane_stride<kND>();  // 2304 floats
+constexpr int kNT0 = kTX * kTY;          // cells of a tile without halo (own-cell operand tiles)
+// float planes: VX, VY, P, T raw, wall, T post-pressure; mbarrier; CTA max |v|
+constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;
+#ifndef WSB_DRY_CTAS
+#define WSB_DRY_CTAS 4   // resident CTAs per SM the register allocation is bounded for
+#endif
 
 // glob: base = base_1 (advection output, pressure pending), wall = wall_1.
-// maps: [0..4] TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box (loads);
-//       [5..8] descriptors of baseOut.c[0..3] with a kTX x kTY box (stores).
-__global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ GlobalCtx glob,
+// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
+// (Tried and dropped, profiles/r2_dry_variants.md: results leaving through shared-memory tiles and
+// TMA box stores — the elected thread's wait for the store to drain keeps the CTA's slot busy, 4 %
+// slower than plain coalesced stores; a persistent grid with double-buffered TMA prefetch of the
+// next tile — hides the load latency completely but fits only 3 CTAs per SM, 7 % slower: the
+// kernel is bound by shared-memory wavefronts and issue slots, not by exposed HBM latency.)
+__global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
-                                                      const __grid_constant__ TileMaps<9> maps, int useTma, int applyPressure,
+                                                      const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
                                                       Planes4 baseOut, unsigned* __restrict__ maxv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sVX = reinterpret_cast<float*>(smem_raw);
@@ -350,14 +396,15 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
   float* sT = sP + kPSD;    // raw T
   int* sWl = reinterpret_cast<int*>(sT + kPSD);
   float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
-  float* sOut = sT2 + kPSD;                            // [4][kNT0] result tiles
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sOut + 4 * kNT0);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
+  unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
   constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kHD;
+  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTYD - kHD;
 
+  if (tid == 0) *sMax = 0u;
   if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -389,8 +436,6 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
   // advection of the base field on the tile
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
-  // full tiles of a TMA-capable grid leave through shared memory and one box store per plane
-  const bool boxStore = WSB_OPT_TMAST && useTma && X0 + kHX + kTX <= g.cx1 && Y0 + kHD + kTY <= g.H;
   float vm = 0.0f;
   if (x < g.cx1) {
     const int gx = global_x(g, x);
@@ -398,7 +443,7 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
     const float fragCoordX = gxf + 0.5f;
     const int lxBase = tx + kHX;
 #pragma unroll 1
-    for (int ty = ty0; ty < kTY; ty += kRowStep) {
+    for (int ty = ty0; ty < kTYD; ty += kRowStep) {
       const int y = Y0 + kHD + ty;
       if (y >= g.H) break;
       const int c = (ty + kHD) * SW + lxBase;
@@ -458,24 +503,10 @@ __global__ void __launch_bounds__(kNT, 4) k_fused_dry(const __grid_constant__ Gl
       } else {  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
         base = make_float4(sVX[c], sVY[c], sP[c], ((w0 & 0xff) == WALLTYPE_LAND) ? 1000.0f : sT2[c]);
       }
-      if (boxStore) {
-        const int t = ty * kTX + tx;
-        sOut[t] = base.x; sOut[kNT0 + t] = base.y; sOut[2 * kNT0 + t] = base.z; sOut[3 * kNT0 + t] = base.w;
-      } else {
-        baseOut.st((size_t)y * g.pitch + x, base);
-      }
+      baseOut.st((size_t)y * g.pitch + x, base);
     }
   }
-  if (boxStore) {  // CTA-uniform
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) tma_store_box(&maps.m[5 + k], X0 + kHX, Y0 + kHD, sOut + k * kNT0);
-      tma_store_commit_wait();
-    }
-  }
-  report_vmax(vm, maxv);
+  report_vmax_cta(vm, maxv, sMax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -602,6 +633,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   __syncthreads();
   sweep_velocity<kSW1, kN1>(d, sVX, sVY, sP, sWl);
   __syncthreads();
+#if WSB_SWEEP_QUAD
   // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
   for (int s = SW + 4 * tid; s < kN1 - 2 * SW; s += 4 * kNT) {
     const float4 vx = ld4(sVX + s), vy = ld4(sVY + s), vxu = ld4(sVX + s + SW);
@@ -621,6 +653,25 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
     st4(sVFY + s - (kH1 - 1) * SW, make_float4(v0.y, v1.y, v2.y, v3.y));
   }
   __syncthreads();
+#else
+  // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
+  for (int s = SW + 2 * tid; s < kN1 - 2 * SW; s += 2 * kNT) {
+    const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vxu = ld2(sVX + s + SW);
+    const float vyr = sVY[s + 2];
+    st2(sCurl + s, make_float2(curl_cell(vx.x, vy.x, vxu.x, vy.y), curl_cell(vx.y, vy.y, vxu.y, vyr)));
+  }
+  __syncthreads();
+  // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
+  // valid for 2 <= i <= SW-4
+  for (int s = (kH1 - 1) * SW + 2 * tid; s < (kH1 + kTY) * SW; s += 2 * kNT) {
+    const float2 c = ld2(sCurl + s), cd = ld2(sCurl + s - SW), cu = ld2(sCurl + s + SW);
+    const float cl = sCurl[s - 1], cr = sCurl[s + 2];
+    const float2 va = vorticity_cell(c.x, cl, cd.x, c.y, cu.x), vb = vorticity_cell(c.y, c.x, cd.y, cr, cu.y);
+    st2(sVFX + s - (kH1 - 1) * SW, make_float2(va.x, vb.x));
+    st2(sVFY + s - (kH1 - 1) * SW, make_float2(va.y, vb.y));
+  }
+  __syncthreads();
+#endif
 
   // S5: boundary pass on the TX x TY interior
 #pragma unroll 1
@@ -702,6 +753,8 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
   const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH2;
 
   // (interior rows never touch the CLAMP_TO_EDGE rule of the light texture, so one box shape serves all planes)
+  unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
+  if (tid == 0) *sMax = 0u;
   if (tile_tma_ok<kSW2, kSH2>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -864,7 +917,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       lightOut.st(ci, lighting_cell(lc, g, d, x, y, base.w, water, wl, TBelow));
     }
   }
-  report_vmax(vm, maxv);
+  report_vmax_cta(vm, maxv, sMax);
 }
 
 // pressure pass on a rectangle, for readbacks of frameBuff_0's base in the fused schedule
