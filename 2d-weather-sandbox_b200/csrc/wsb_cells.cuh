@@ -162,7 +162,11 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
     float precipEvaporation = gmax(fb.z, 0.0f);
     water.x += precipEvaporation;
     water.z = gmax(water.z * 0.997f - 0.00001f + fb.x * 0.005f, 0.0f);               // :115
-    water.w /= 1.0f + gmax(-fb.z * 0.1f, 0.0f) + fb.x * 0.000f;                       // :119
+    {  // :119  smoke is washed out by precipitation; x / 1.0f == x exactly, so the IEEE division
+       // sequence is skipped wherever no precipitation feedback arrived (almost every cell)
+      const float washout = 1.0f + gmax(-fb.z * 0.1f, 0.0f) + fb.x * 0.000f;
+      if (washout != 1.0f) water.w /= washout;
+    }
     water.w -= fb.x * 0.0001f;                                                         // :121
     water.w -= gmax((water.w - 4.0f) * 0.01f, 0.0f);                                   // :124
     water.w = gmax(water.w, 0.0f);                                                     // :126
