@@ -52,41 +52,52 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU through NVML while a timed region runs.
+    NVML is initialised in the constructor (it can take longer than a 50 ms timed region); the
+    thread then samples every 5 ms until result() is called."""
+
+    NAMES = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4, "hw_power_brake": 0x80}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, threading.Event()
-        self.sm, self.reasons, self.sm_max, self.err = [], set(), None, None
-
-    def run(self):
+        self.sm, self.reasons, self.sm_max, self.err, self.nv, self.h = [], set(), None, None, None, None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            names = {
-                "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
-                "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
-            }
-            while not self.stop_flag.is_set():
-                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                    for k, bit in names.items():
-                        if mask & bit:
-                            self.reasons.add(k)
-                except Exception:
-                    pass
-                time.sleep(0.05)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception as e:  # NVML missing: fall back to one nvidia-smi sample
             self.err = repr(e)
 
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for k, bit in self.NAMES.items():
+                if mask & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
+            while not self.stop_flag.is_set():
+                self._sample()
+                time.sleep(0.005)
+        except Exception as e:
+            self.err = repr(e)
+
     def result(self):
+        if self.nv is not None and self.is_alive():
+            try:
+                self._sample()  # one more while the GPU is still under load / just finished
+            except Exception:
+                pass
         self.stop_flag.set()
         self.join(timeout=2)
         if not self.sm:
@@ -95,10 +106,11 @@ class ClockSampler(threading.Thread):
 
                 out = subprocess.check_output(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
                                                "--format=csv,noheader,nounits"], text=True).strip().split(",")
-                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "note": "single nvidia-smi sample after the run"}
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "note": f"single nvidia-smi sample after the run ({self.err})"}
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": f"no clock source: {self.err}"}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_min_mhz": float(min(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def _ncu_traffic(kernel: str, W: int, H: int, world: int):
@@ -314,7 +326,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
 
     if world == 1 and rank == 0:
-        line["dry_sweep"] = dry_sweep_leg(W, H, K, Wm, peak, local_rank)
+        line["dry_sweep"] = dry_sweep_leg(W, H, K, Wm, peak, local_rank, prewarm=not args.no_prewarm)
         if args.particles:
             line["with_particles"] = particles_leg(W, H, K, Wm, local_rank)
         if not args.no_cpu:
@@ -328,7 +340,7 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
-def dry_sweep_leg(W, H, K, Wm, peak, device_index):
+def dry_sweep_leg(W, H, K, Wm, peak, device_index, prewarm=True):
     """The fused pressure+velocity+advection sweep (k_fused_dry) at the same grid: the kernel the
     >= 70 % HBM-roofline target of BASELINE.json is stated on."""
     import wsb200
@@ -340,12 +352,16 @@ def dry_sweep_leg(W, H, K, Wm, peak, device_index):
     sim.upload(base, water, wall)
     del base, water, wall
     sim.set_profiling(True)
-    sim.step_dry(4 * PREWARM_ITERS)  # clock ramp-up after the host-side state generation
-    sim.sync()
+    if prewarm:
+        sim.step_dry(4 * PREWARM_ITERS)  # clock ramp-up after the host-side state generation
+        sim.sync()
     sim.step_dry(Wm)
     sim.sync()
+    sampler = ClockSampler(device_index)
+    sampler.start()
     sim.step_dry(K)
     sim.sync()
+    clocks = sampler.result()
     ms = sim.last_step_ms()
     t, c = sim.kernel_time_ms(S.KERNEL_DRY)
     per = t / max(c, 1)
@@ -353,7 +369,7 @@ def dry_sweep_leg(W, H, K, Wm, peak, device_index):
     out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
            "roofline": {"bound": "hbm", "kernel": "k_fused_dry", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": _ncu_traffic("k_fused_dry", W, H, 1), "alg_bytes_per_cell": B_ALG["k_fused_dry"], "avg_launch_ms": per},
-           "max_abs_velocity_cells_per_iter": sim.max_velocity}
+           "max_abs_velocity_cells_per_iter": sim.max_velocity, "clocks": clocks}
     sim.close()
     return out
 
