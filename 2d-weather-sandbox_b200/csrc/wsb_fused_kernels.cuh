@@ -299,7 +299,9 @@ __device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sV
 }
 // velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
 template <int SW, int N>
-__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl) {
+__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl,
+                                               unsigned* sAnyWall = nullptr) {
+  bool any = false;
   for (int s = SW + 4 * (int)threadIdx.x; s < N - SW; s += 4 * kNT) {
     float4 vx = ld4(sVX + s), vy = ld4(sVY + s);
     const float4 P = ld4(sP + s), Pu = ld4(sP + s + SW);
@@ -309,9 +311,11 @@ __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, f
     velocity_cell(d, vx.y, vy.y, P.y, P.z, Pu.y, wl_is_wall(w.y) ? 0 : 1);
     velocity_cell(d, vx.z, vy.z, P.z, P.w, Pu.z, wl_is_wall(w.z) ? 0 : 1);
     velocity_cell(d, vx.w, vy.w, P.w, Pr, Pu.w, wl_is_wall(w.w) ? 0 : 1);
+    any |= wl_is_wall(w.x) | wl_is_wall(w.y) | wl_is_wall(w.z) | wl_is_wall(w.w);
     st4(sVX + s, vx);
     st4(sVY + s, vy);
   }
+  if (sAnyWall && __any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *sAnyWall = 1u;
 }
 
 #else
@@ -338,18 +342,25 @@ __device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sV
   }
 }
 // velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
+// sAnyWall (optional, zeroed by the caller before an earlier barrier): set to 1 when any cell of
+// the swept rows is a wall, so that the per-cell pass can drop its wall tests on all-air tiles.
 template <int SW, int N>
-__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl) {
+__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl,
+                                               unsigned* sAnyWall = nullptr) {
+  bool any = false;
   for (int s = SW + 2 * (int)threadIdx.x; s < N - SW; s += 2 * kNT) {
     float2 vx = ld2(sVX + s), vy = ld2(sVY + s);
     const float2 P = ld2(sP + s), Pu = ld2(sP + s + SW);
     const float Pr = sP[s + 2];
     const int2 w = ld2(sWl + s);
-    velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wl_is_wall(w.x) ? 0 : 1);
-    velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wl_is_wall(w.y) ? 0 : 1);
+    const bool wa = wl_is_wall(w.x), wb = wl_is_wall(w.y);
+    any |= wa | wb;
+    velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wa ? 0 : 1);
+    velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wb ? 0 : 1);
     st2(sVX + s, vx);
     st2(sVY + s, vy);
   }
+  if (sAnyWall && __any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *sAnyWall = 1u;
 }
 
 #endif
@@ -398,13 +409,14 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
   float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
   unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
+  unsigned* sAnyWall = sMax + 1;                            // any wall cell in staged rows 1 .. SH-2
   constexpr int SW = kSWD;
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
   const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTYD - kHD;
 
-  if (tid == 0) *sMax = 0u;
+  if (tid == 0) { *sMax = 0u; *sAnyWall = 0u; }
   if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -430,10 +442,17 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
 
   sweep_pressure<kSWD, kND>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
   __syncthreads();
-  sweep_velocity<kSWD, kND>(d, sVX, sVY, sP, sWl);
+  sweep_velocity<kSWD, kND>(d, sVX, sVY, sP, sWl, sAnyWall);
   __syncthreads();
 
-  // advection of the base field on the tile
+  // advection of the base field on the tile.  On an all-air tile (most of the atmosphere) the own
+  // cell's wall test and the wall-aware bilerp weights fall away: every tap of a near back-trace
+  // lies in the rows the velocity sweep has just looked at.
+#if WSB_OPT_AIRFAST
+  const bool walls = *sAnyWall != 0u;
+#else
+  const bool walls = true;
+#endif
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
   float vm = 0.0f;
@@ -449,7 +468,8 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
       const int c = (ty + kHD) * SW + lxBase;
       const float gyf = (float)y;
       const float fragCoordY = gyf + 0.5f;
-      const int w0 = sWl[c];
+      int w0 = 0x0100;  // an air texel (DISTANCE 1)
+      if (walls) w0 = sWl[c];
       float4 base;
       if (!wl_is_wall(w0)) {
         const float vx00 = sVX[c], vy00 = sVY[c];
@@ -469,7 +489,8 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
           const float* q3 = near_ptr(n3, pc, pc - SW);
           base.x = mix2d(q1[0], q1[1], q1[SW], q1[SW + 1], n1.fx, n1.fx, n1.fy);
           base.y = mix2d(q2[0], q2[1], q2[SW], q2[SW + 1], n2.fx, n2.fx, n2.fy);
-          const WallMix m = tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 4 * kPSD), 0, n3.fx, n3.fy);
+          const WallMix m = walls ? tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 4 * kPSD), 0, n3.fx, n3.fy)
+                                  : WallMix{n3.fx, n3.fx, n3.fy};
           const float* qP = q3 + 2 * kPSD;
           const float* qT = q3 + 5 * kPSD;
           base.z = mix2d(qP[0], qP[1], qP[SW], qP[SW + 1], m.ab, m.cd, m.abcd);
