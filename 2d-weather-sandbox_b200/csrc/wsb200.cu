@@ -655,7 +655,7 @@ const char* wsb_build_info(void) {
 #define WSB_STR2(x) #x
 #define WSB_STR(x) WSB_STR2(x)
   return "libwsb200 abi 1 | sm_100a | nvcc " WSB_STR(__CUDACC_VER_MAJOR__) "." WSB_STR(__CUDACC_VER_MINOR__) "." WSB_STR(__CUDACC_VER_BUILD__)
-         " | fmad=false | tile 64x16, 256 threads, TMA-staged channel planes | ghost 8";
+         " | fmad=false | tile 64x16 (dry sweep 64x28), 256 threads, TMA-staged channel planes | ghost 8";
 }
 
 int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]) {
