@@ -1,7 +1,7 @@
 """Independent restatement of the precipitation-particle pass (precipitationShader.vert:66-298,
 precipitationShader.frag, app.js:5933-5952) as a scalar, droplet-by-droplet Python transliteration
 of the GLSL: random respawn sampling (common.glsl:103-137 hash / random2d), spawn chance, lightning
-spawn, growth / freezing / melting / evaporation with their feedback to the fluid, fall and
+spawn and latch (lightningLocationShader.frag), the inactive-droplet count latch, growth / freezing / melting / evaporation with their feedback to the fluid, fall and
 horizontal wrap, deposition on the ground; then the frozen rasterisation rule of DESIGN.md 2
 (point sprites cover the pixels whose centre lies in [c - size/2, c + size/2), clipped, never
 wrapped, `out` varyings start at zero, blend ONE, ONE in droplet order) and pow(m, 1/3) as the
@@ -238,16 +238,16 @@ def precipitation(base1, water1, drops, lightning, p, iter_num, inactive):
     return out, fb_tex, dep_tex, seen
 
 
-@pytest.mark.parametrize("seed,iter_num", [(3, 205), (8, 600), (12, 41)])
-def test_precipitation_pass_matches_python_transliteration(seed, iter_num):
+@pytest.mark.parametrize("seed,iter_num,cold_cloud", [(3, 205, 30.0), (8, 600, 30.0), (12, 41, 30.0), (20, 77, 7.0)])
+def test_precipitation_pass_matches_python_transliteration(seed, iter_num, cold_cloud):
     w, h = 64, 48
     g, base, water, wall, _ = stress_state(w, h, seed=seed)
     g["enablePrecipitation"] = True
     rng = np.random.default_rng(seed)
     # dense, cold cloud aloft: spawning and lightning become likely enough to be exercised
     air = wall[..., 1] != 0
-    water[h // 2:, :, 1] += np.where(air[h // 2:], f32(30.0), f32(0.0))
-    water[h // 2:, :, 0] += np.where(air[h // 2:], f32(30.0), f32(0.0))
+    water[h // 2:, :, 1] += np.where(air[h // 2:], f32(cold_cloud), f32(0.0))
+    water[h // 2:, :, 0] += np.where(air[h // 2:], f32(cold_cloud), f32(0.0))
     water[:h // 5, :, 1] += np.where(air[:h // 5], f32(40.0), f32(0.0))   # warm dense cloud near the ground: rain spawns
     water[:h // 5, :, 0] += np.where(air[:h // 5], f32(40.0), f32(0.0))
     n = 400
@@ -286,6 +286,17 @@ def test_precipitation_pass_matches_python_transliteration(seed, iter_num):
     got_fb, got_dep = ora.field(O.FIELD_FEEDBACK), ora.field(O.FIELD_DEPOSITION)
     assert np.array_equal(got_dep, want_dep), f"deposition differs in {(got_dep != want_dep).sum()} values"
     assert np.array_equal(got_fb, want_fb), f"feedback differs in {(got_fb != want_fb).sum()} values"
+    # lightningLocationShader.frag:24-38: pixel (1, 0) of the feedback texture is latched unless it holds no strike
+    # of this iteration (or two of them, which doubles START_ITERNUM); app.js:5957-5967: the count of inactive
+    # droplets in pixel (0, 0) becomes the uniform every 600 iterations
+    new = want_fb[0, 1]
+    it = f32(iter_num)
+    discard = new[2] < gmax(it - ONE, ONE) or new[2] > it
+    want_lightning = np.asarray(lightning, f32) if discard else new
+    assert np.array_equal(ora.lightning, want_lightning), f"lightning latch {ora.lightning} vs {want_lightning} ({seen['lightning']} spawned)"
+    assert ora.inactive_droplets == (want_fb[0, 0, 0] if iter_num % 600 == 0 else 3.0)
+    if cold_cloud < 10.0:  # the case chosen to spawn exactly one bolt: it must be latched
+        assert seen["lightning"] == 1 and not discard and ora.lightning[2] == it - f32(0.15)
     missing = [k for k, v in seen.items() if v == 0 and k not in ("lightning",)]
     assert not missing, f"branches not exercised: {missing} ({seen})"
     print(seen)
