@@ -50,7 +50,7 @@ def _map_range_c(v, min1, max1, min2, max2):
     return _clamp(_map_range(v, min1, max1, min2, max2), _gmin(min2, max2), _gmax(min2, max2))
 
 
-def _advection(base, water, wall, p, snd_t, snd_w, snd_v):
+def _advection(base, water, wall, p, snd_t, snd_w, snd_v, marker=True):
     h, w = base.shape[:2]
     texel_y_uniform = f32(1.0 / h)                     # uniform texelSize (app.js:5436)
     ltexel_y = f32(1.0) / f32(h)                       # :69  texelSize = vec2(1.) / resolution
@@ -127,8 +127,9 @@ def _advection(base, water, wall, p, snd_t, snd_w, snd_v):
     evap_on = above_air & (ww[..., 2] > 0) & (temp_c > 0)
     evap = _gmax((_max_water(temp_c + f32(273.15)) - ww[..., 0]) * f32(0.00001), f32(0.0))
     ww[..., 2] = np.where(evap_on, ww[..., 2] - evap, ww[..., 2])
-    # :402-411  wall marker in TOTAL
-    ww[..., 0] = np.where(wall[..., 0] == WATER, f32(1002.0), f32(1001.0))
+    # :402-411  wall marker in TOTAL (after the user-input block, which may build or remove walls)
+    if marker:
+        ww[..., 0] = np.where(wall[..., 0] == WATER, f32(1002.0), f32(1001.0))
 
     is_wall = (wall[..., 1] == 0)[..., None]
     return np.where(is_wall, wb, b), np.where(is_wall, ww, wt), np.where(is_wall, wl, wall)
