@@ -23,9 +23,9 @@
 // of the reference's REPEAT textures (the outermost ring of tiles) — or grids whose row pitch is
 // not a multiple of 16 bytes — take a register-staged fallback (stage_tile) with explicit wrap.
 // Stencil passes then sweep the staged planes in place; the final per-cell pass gathers with
-// plain shared-memory indices, one wavefront per gather.  A back-trace that leaves the halo
-// (|v| >= 1 cell / iteration, never seen in the shipped saves) takes an exact, slow global-memory
-// path.
+// plain shared-memory indices, one wavefront per gather.  A cell with a velocity component of
+// 0.9 cells / iteration or more (never seen in the shipped saves, which peak at 0.36) takes an
+// exact, slow global-memory path instead of the near back-trace (near_tap below).
 #pragma once
 #include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time)
 
