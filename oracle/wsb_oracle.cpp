@@ -10,7 +10,11 @@
 // in this environment (no node / browser / GL / SwiftShader).  The oracle is therefore written
 // from the shader sources alone, one function per reference pass, each citing the file:line it
 // follows.  Where GLSL/WebGL leaves behaviour implementation-defined the canonical choice is
-// written next to the code (and listed in DESIGN.md "Spec freeze").
+// written next to the code (and listed in DESIGN.md "Spec freeze").  What pins it short of the
+// reference itself: every pass is reproduced bit for bit by a second, independent Python
+// restatement of its shader (tests/test_oracle_numpy_*.py, tests/test_oracle_python_*.py;
+// DESIGN.md 6 has the table), which catches transcription slips and disagreements between two
+// readings of the GLSL, not a shared misreading of what a WebGL implementation does.
 //
 // Arithmetic is fp32 with no contraction (build with -ffp-contract=off) so that the CUDA kernels
 // (built with -fmad=false) can reproduce it operation for operation.
