@@ -82,6 +82,7 @@ struct GlobalAt {
   __device__ __forceinline__ float2 dep2() const { return c.dep[(size_t)y * c.g.pitch + x]; }
 };
 
+#ifdef __CUDACC__  // kernels: device only (GlobalCtx / GlobalAt above also compile for the host, tests/host_cells)
 #define WSB_CELL_XY                                   \
   const int x = g.cx0 + blockIdx.x * blockDim.x + threadIdx.x; \
   const int y = blockIdx.y * blockDim.y + threadIdx.y;          \
@@ -174,5 +175,6 @@ __global__ void k_planes_to_texels(Planes4 src, int pitch, int x0, int y0, int w
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i < w && j < h) dst[(size_t)j * w + i] = src.ld((size_t)(y0 + j) * pitch + x0 + i);
 }
+#endif  // __CUDACC__
 
 }  // namespace wsb

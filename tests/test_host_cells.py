@@ -1,0 +1,131 @@
+"""The product's per-cell bodies (csrc/wsb_cells.cuh, wsb_math.cuh, GlobalCtx / GlobalAt of
+wsb_ref_kernels.cuh) compiled for the HOST (tests/host_cells/, g++ -ffp-contract=off) and driven
+through the reference schedule must reproduce the oracle bit for bit — on the CPU, without a GPU.
+What is left for the GPU parity tests to establish is then only the tile plumbing of the kernels
+(staging, halos, indices), not the cell arithmetic.  Test infrastructure: nothing in the product
+loads tests/host_cells/libhostcells.so."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import wsb200
+from oracle import oracle as O
+
+from util import make_oracle, stress_state
+
+P = wsb200.params
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_cells")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.check_call(["make", "-C", HERE, "-s"])
+    L = ctypes.CDLL(os.path.join(HERE, "libhostcells.so"))
+    vp = ctypes.c_void_p
+    L.hc_create.restype = vp
+    L.hc_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.hc_destroy.argtypes = [vp]
+    L.hc_upload.argtypes = [vp, vp, vp, vp]
+    L.hc_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
+    L.hc_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
+    L.hc_set_profiles.argtypes = [vp, vp, vp, vp, vp]
+    L.hc_set_iter.argtypes = [vp, ctypes.c_longlong]
+    L.hc_set_feedback.argtypes = [vp, vp, vp]
+    L.hc_run_pass.argtypes = [vp, ctypes.c_int]
+    L.hc_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class HostCells:
+    def __init__(self, L, g, base, water, wall, fi=None, profiles=None):
+        self.L, (self.h_, self.w_) = L, base.shape[:2]
+        self.h = L.hc_create(self.w_, self.h_)
+        b, w, wl = (np.ascontiguousarray(a) for a in (base, water, wall))
+        L.hc_upload(self.h, _ptr(b), _ptr(w), _ptr(wl))
+        p = P.derive_params(g)
+        L.hc_set_params(self.h, ctypes.byref(p))
+        fi = fi if fi is not None else P.frame_inputs(g)
+        L.hc_set_frame_inputs(self.h, ctypes.byref(fi))
+        prof = [np.ascontiguousarray(a, np.float32) for a in (profiles or (P.initial_T_profile(self.h_, g),))]
+        prof += [np.zeros(self.h_ + 1, np.float32)] * (4 - len(prof))
+        L.hc_set_profiles(self.h, *(_ptr(a) for a in prof))
+
+    def run(self, p):
+        self.L.hc_run_pass(self.h, p)
+
+    def read(self, field, buf):
+        if field == 2:
+            out = np.empty((self.h_, self.w_, 4), np.int8)
+        else:
+            out = np.empty((self.h_, self.w_, 4), np.float32)
+        self.L.hc_read(self.h, field, buf, _ptr(out))
+        return out
+
+    def close(self):
+        self.L.hc_destroy(self.h)
+
+
+FIELDS = (("base", 0, O.FIELD_BASE), ("water", 1, O.FIELD_WATER), ("wall", 2, O.FIELD_WALL), ("light", 3, O.FIELD_LIGHT))
+
+
+def _compare(hc, ora, what):
+    for name, f, of in FIELDS:
+        for buf in (0, 1):
+            got, want = hc.read(f, buf), ora.field(of, buf)
+            same = (got == want) | ((got != got) & (want != want)) if got.dtype != np.int8 else got == want
+            assert same.all(), f"{what}: {name}_{buf} differs in {(~same).sum()} values, first at {np.argwhere(~same)[0]}"
+
+
+@pytest.mark.parametrize("shape,seed", [((96, 48), 3), ((133, 61), 11)])
+def test_cell_headers_on_the_host_reproduce_the_oracle(lib, shape, seed):
+    w, h = shape
+    g, base, water, wall, _ = stress_state(w, h, seed=seed)
+    g["enablePrecipitation"] = False
+    g["globalDrying"], g["globalHeating"], g["soundingForcing"] = 0.00002, 0.0003, 0.95
+    rng = np.random.default_rng(seed)
+    prof = (P.initial_T_profile(h, g), (300 + rng.uniform(-5, 5, h + 1)).astype(np.float32), rng.uniform(0, 20, h + 1).astype(np.float32),
+            rng.uniform(-0.2, 0.2, h + 1).astype(np.float32))
+    ora = make_oracle(g, base, water, wall, None)
+    ora.set_profiles(*prof)
+    hc = HostCells(lib, g, base, water, wall, profiles=prof)
+    for it in range(25):
+        for p in (0, 1, 2, 3, 4, 5, 6, 8):
+            ora.run_pass(p)
+            hc.run(p)
+            if it in (0, 24):
+                _compare(hc, ora, f"iteration {it}, pass {p}")
+    _compare(hc, ora, "after 25 iterations")
+    assert np.isfinite(hc.read(0, 0)).all()
+    hc.close()
+
+
+def test_cell_headers_user_input_and_slow_processes(lib):
+    """Brush + airplane inputs and the iteration-multiple processes of the boundary pass."""
+    w, h = 80, 40
+    g, base, water, wall, _ = stress_state(w, h, seed=5)
+    g["enablePrecipitation"] = False
+    for kind, intensity, it0 in ((1, 0.7, 98), (2, 0.3, 199), (4, 0.8, 19), (11, 1.0, 0), (12, -1.0, 599), (22, 1.0, 39), (0, 0.0, 100)):
+        fi = P.frame_inputs(g)
+        fi.userInputType = kind
+        for k, v in enumerate((0.4, 0.2, intensity, 9.0)):
+            fi.userInputValues[k] = v
+        fi.userInputMove[0], fi.userInputMove[1] = 0.02, -0.01
+        for k, v in enumerate((0.6, 0.3, 1.0, -1.0 if kind != 0 else 1.0)):
+            fi.airplaneValues[k] = v
+        ora = make_oracle(g, base, water, wall, None, fi=fi)
+        hc = HostCells(lib, g, base, water, wall, fi=fi)
+        ora.iter = it0
+        lib.hc_set_iter(hc.h, it0)
+        for it in range(3):
+            for p in (0, 1, 2, 3, 4, 5, 6, 8):
+                ora.run_pass(p)
+                hc.run(p)
+        _compare(hc, ora, f"tool {kind} from iteration {it0}")
+        hc.close()
