@@ -718,9 +718,11 @@ __device__ void advection_cell(const C& c, const Geom& g, const DevParams& d, co
 //   Ctx: float lightS(x,y) SUNLIGHT with x wrapped, y already clamped by the caller;
 //        float lightIRdown(x,y), lightIRup(x,y).
 //   T, water, wall: this cell AFTER the advection pass; TBelow: base_1 T of the cell below.
+//   fragCoordX: (float)global_x(g, x) + 0.5f — a per-thread constant of the fused kernel, passed
+//   in so that the periodic wrap of the column is not redone for every cell.
 // ---------------------------------------------------------------------------------------------
 template <class C>
-__device__ float4 lighting_cell(const C& c, const Geom& g, const DevParams& d, int x, int y, float T, float4 water,
+__device__ float4 lighting_cell(const C& c, const Geom& g, const DevParams& d, int x, int y, float fragCoordX, float T, float4 water,
                                 char4 wall, float TBelow) {
   const float fragCoordY = (float)y + 0.5f;
   if (fragCoordY >= g.Hf - 1.0f) return make_float4(d.in.sunIntensity, 0.0f, 0.0f, 0.0f);  // :40
@@ -728,12 +730,12 @@ __device__ float4 lighting_cell(const C& c, const Geom& g, const DevParams& d, i
   const float cellHeightCompensation = g.cellHeightComp;  // 300.0f / g.Hf
   float sunlight;
   {  // :48-49, canonical fp32 bilinear in pixel space, wrap S = REPEAT, wrap T = CLAMP_TO_EDGE
-    const int gx = global_x(g, x);
-    float px = ((float)gx + 0.5f) + d.sinSun, py = fragCoordY + d.cosSun;
+    float px = fragCoordX + d.sinSun, py = fragCoordY + d.cosSun;
     float stx = px - 0.5f, sty = py - 0.5f;
     float flx = floorf(stx), fly = floorf(sty);
     float fx = stx - flx, fy = sty - fly;
-    int ix = x + ((int)flx - gx), iy = (int)fly;
+    // column offset of the tap relative to this cell: (fragCoordX - 0.5f) is the global column, exactly
+    int ix = x + (int)(flx - (fragCoordX - 0.5f)), iy = (int)fly;
     int y0 = min(max(iy, 0), g.H - 1), y1 = min(max(iy + 1, 0), g.H - 1);
     sunlight = gmix(gmix(c.lightS(ix, y0), c.lightS(ix + 1, y0), fx), gmix(c.lightS(ix, y1), c.lightS(ix + 1, y1), fx), fy);
   }

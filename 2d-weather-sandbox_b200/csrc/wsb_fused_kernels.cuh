@@ -935,7 +935,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
           TBelow = o.base.w;
         }
       }
-      lightOut.st(ci, lighting_cell(lc, g, d, x, y, base.w, water, wl, TBelow));
+      lightOut.st(ci, lighting_cell(lc, g, d, x, y, fragCoordX, base.w, water, wl, TBelow));
     }
   }
   report_vmax_cta(vm, maxv, sMax);

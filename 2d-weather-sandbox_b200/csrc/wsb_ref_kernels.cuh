@@ -160,7 +160,8 @@ __global__ void k_ref_pressure(GlobalCtx c, Planes4 baseOut, int* __restrict__ w
 __global__ void k_ref_lighting(GlobalCtx c, DevParams d, Planes4 lightOut) {
   const Geom& g = c.g;
   WSB_CELL_XY
-  lightOut.st(ci, lighting_cell(c, g, d, x, y, c.base.c[3][ci], c.water.ld(ci), as_char4(c.wall[ci]), c.bt(x, y - 1)));
+  lightOut.st(ci, lighting_cell(c, g, d, x, y, (float)global_x(g, x) + 0.5f, c.base.c[3][ci], c.water.ld(ci), as_char4(c.wall[ci]),
+                                c.bt(x, y - 1)));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -189,7 +189,8 @@ void hc_run_pass(void* h, int pass) {
       GlobalCtx c = ctx(s, 1, 1, 1, src);
       for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
         const size_t ci = (size_t)y * W + x;
-        s.light[dst].p.st(ci, lighting_cell(c, g, s.dp, x, y, c.base.c[3][ci], c.water.ld(ci), as_char4(c.wall[ci]), c.bt(x, y - 1)));
+        s.light[dst].p.st(ci, lighting_cell(c, g, s.dp, x, y, (float)global_x(g, x) + 0.5f, c.base.c[3][ci], c.water.ld(ci),
+                                            as_char4(c.wall[ci]), c.bt(x, y - 1)));
       }
       s.even = !s.even;
       break;
