@@ -52,7 +52,7 @@ __device__ __forceinline__ float potentialToRealT(const DevParams& d, float pot,
   return pot - texCoordY * d.p.dryLapse;  // common.glsl:151-153
 }
 
-#ifdef __CUDACC__  // warp / CTA collectives: device only (the cell bodies below also compile for the host, tests/host_cells)
+#if defined(__CUDACC__) || defined(WSB_HOST_EMU)  // warp / CTA collectives: device, or the host emulation of tests/host_cells (the cell bodies below compile for the plain host too)
 // Largest |v| component seen by advection since the upload — a RUNNING maximum, so the global
 // atomic is only issued by whoever holds something larger than the current value (one L2 read
 // otherwise).  Measured (profiles/r2_vmax_atomics.md): an unconditional same-address atomicMax per
@@ -82,7 +82,7 @@ __device__ __forceinline__ void report_vmax_cta(float vm, unsigned* __restrict__
     if (v > __ldcg(maxv)) atomicMax(maxv, v);
   }
 }
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || WSB_HOST_EMU
 
 // ---------------------------------------------------------------------------------------------
 // velocityShader.frag:32-62

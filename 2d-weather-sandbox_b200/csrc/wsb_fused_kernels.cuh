@@ -27,7 +27,13 @@
 // 0.9 cells / iteration or more (never seen in the shipped saves, which peak at 0.36) takes an
 // exact, slow global-memory path instead of the near back-trace (near_tap below).
 #pragma once
+#ifndef WSB_HOST_EMU
 #include <cuda.h>  // CUtensorMap (type only; the encoder is resolved at run time)
+#endif
+// WSB_HOST_EMU: tests/host_cells/ compiles this file for the HOST (one OS thread per CUDA thread,
+// TMA boxes and mbarriers emulated by emu::) so that the tile plumbing of the kernels — staging,
+// halos, sweeps, indices, the near back-trace — is checked against the oracle on the CPU.  Test
+// infrastructure only: the emulation header defines CUtensorMap, threadIdx, __syncthreads, ...
 
 #include "wsb_cells.cuh"
 #include "wsb_ref_kernels.cuh"
@@ -53,6 +59,7 @@ __device__ __forceinline__ bool wl_is_land_wall(int w) { return (w & 0xffff) == 
 template <int N>
 struct TileMaps { CUtensorMap m[N]; };  // passed as a __grid_constant__ kernel parameter
 
+#ifndef WSB_HOST_EMU
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
@@ -79,6 +86,14 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
                "l"(map), "r"(x), "r"(y), "r"(smem_addr(bar))
                : "memory");
 }
+#define WSB_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#else  // host emulation of the five primitives above (tests/host_cells/cuda_emu.h)
+inline void mbar_init(unsigned long long* bar, unsigned count) { emu::mbar_init(bar, count); }
+inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu::mbar_expect_tx(bar, bytes); }
+inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu::mbar_wait(bar, parity); }
+inline void tma_load_box(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) { emu::tma_load_box(dst, map, x, y, bar); }
+#define WSB_DYN_SMEM(name) unsigned char* name = emu::dyn_smem()
+#endif
 // compile-time switches for A/B timing (make variant OUT=... EXTRA="-DWSB_OPT_NEAR=0 ...", profiles/tools/)
 #ifndef WSB_OPT_NEAR
 #define WSB_OPT_NEAR 1      // back-trace taps relative to the own cell when every |v| < 0.9
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
                                                       const __grid_constant__ DevParams d,
                                                       const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
                                                       Planes4 baseOut, unsigned* __restrict__ maxv) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WSB_DYN_SMEM(smem_raw);
   float* sVX = reinterpret_cast<float*>(smem_raw);
   float* sVY = sVX + kPSD;
   float* sP = sVY + kPSD;
@@ -594,7 +609,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
                                                       const float* __restrict__ initial_T, int applyPressure, int useFb,
                                                       float4* fb, float2* dep, Planes4 baseOut, Planes4 waterOut,
                                                       int* __restrict__ wallOut) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WSB_DYN_SMEM(smem_raw);
   float* sVX = reinterpret_cast<float*>(smem_raw);
   float* sVY = sVX + kPS1;
   float* sP = sVY + kPS1;
@@ -753,7 +768,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
                                                       const float* __restrict__ sndW, const float* __restrict__ sndV,
                                                       Planes4 baseOut, Planes4 waterOut, int* __restrict__ wallOut,
                                                       Planes4 lightOut, unsigned* __restrict__ maxv) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WSB_DYN_SMEM(smem_raw);
   float* sVX = reinterpret_cast<float*>(smem_raw);
   float* sVY = sVX + kPS2;
   float* sP = sVY + kPS2;

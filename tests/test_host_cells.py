@@ -129,3 +129,110 @@ def test_cell_headers_user_input_and_slow_processes(lib):
                 hc.run(p)
         _compare(hc, ora, f"tool {kind} from iteration {it0}")
         hc.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the fused kernels themselves, on a host emulation of the CUDA execution model
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-C", HERE, "-s", "libemufused.so"])
+    L = ctypes.CDLL(os.path.join(HERE, "libemufused.so"))
+    vp = ctypes.c_void_p
+    L.ef_create.restype = vp
+    L.ef_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ef_destroy.argtypes = [vp]
+    L.ef_upload.argtypes = [vp, vp, vp, vp]
+    L.ef_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
+    L.ef_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
+    L.ef_set_profiles.argtypes = [vp, vp, vp, vp, vp]
+    L.ef_set_iter.argtypes = [vp, ctypes.c_longlong]
+    L.ef_uses_tma.argtypes = [vp]
+    L.ef_step.argtypes = [vp, ctypes.c_int]
+    L.ef_step_dry.argtypes = [vp, ctypes.c_int]
+    L.ef_max_velocity.argtypes = [vp]
+    L.ef_max_velocity.restype = ctypes.c_float
+    L.ef_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    return L
+
+
+class EmuFused:
+    """The FUSED schedule on the emulator, with the read-back views of wsb_read_rect."""
+
+    def __init__(self, L, g, base, water, wall, fi=None, profiles=None):
+        self.L, (self.h_, self.w_) = L, base.shape[:2]
+        self.h = L.ef_create(self.w_, self.h_)
+        b, w, wl = (np.ascontiguousarray(a) for a in (base, water, wall))
+        L.ef_upload(self.h, _ptr(b), _ptr(w), _ptr(wl))
+        p = P.derive_params(g)
+        L.ef_set_params(self.h, ctypes.byref(p))
+        fi = fi if fi is not None else P.frame_inputs(g)
+        L.ef_set_frame_inputs(self.h, ctypes.byref(fi))
+        prof = [np.ascontiguousarray(a, np.float32) for a in (profiles or (P.initial_T_profile(self.h_, g),))]
+        prof += [np.zeros(self.h_ + 1, np.float32)] * (4 - len(prof))
+        L.ef_set_profiles(self.h, *(_ptr(a) for a in prof))
+
+    def read(self, field, view):
+        out = np.empty((self.h_, self.w_, 4), np.int8 if field == 2 else np.float32)
+        self.L.ef_read(self.h, field, view, _ptr(out))
+        return out
+
+    def close(self):
+        self.L.ef_destroy(self.h)
+
+
+def _compare_fused(em, ora, what):
+    """Canonical state after whole iterations (tests/test_gpu_parity.py: _assert_fields_equal)."""
+    pairs = (("base", em.read(0, 0), ora.field(O.FIELD_BASE, 0)), ("water1", em.read(1, 1), ora.field(O.FIELD_WATER, 1)),
+             ("water0", em.read(1, 0), ora.field(O.FIELD_WATER, 0)), ("wall", em.read(2, 0), ora.field(O.FIELD_WALL, 0)),
+             ("light", em.read(3, 2), ora.light_latest()), ("light0", em.read(3, 0), ora.field(O.FIELD_LIGHT, 0)))
+    for name, got, want in pairs:
+        same = got == want
+        assert same.all(), f"{what}: {name} differs in {(~same).sum()} values, first at {np.argwhere(~same)[0]}: {got[~same][0]!r} vs {want[~same][0]!r}"
+
+
+@pytest.mark.parametrize("shape,seed", [((192, 96), 7), ((100, 100), 3), ((333, 77), 5), ((256, 40), 9)])
+def test_fused_kernels_on_the_emulator_reproduce_the_oracle(emu, shape, seed):
+    """Full physics, grids with and without TMA-capable tiles, ragged edges, walls in the flow."""
+    w, h = shape
+    g, base, water, wall, _ = stress_state(w, h, seed=seed)
+    g["enablePrecipitation"] = False
+    ora = make_oracle(g, base, water, wall, None)
+    em = EmuFused(emu, g, base, water, wall)
+    assert bool(emu.ef_uses_tma(em.h)) == (w % 4 == 0 and w >= 72 and h >= 32)
+    done = 0
+    for n in (1, 2, 6):
+        ora.step(n - done)
+        emu.ef_step(em.h, n - done)
+        done = n
+        _compare_fused(em, ora, f"{shape} after {n} iterations")
+    assert 0 < emu.ef_max_velocity(em.h) < 1.0
+    em.close()
+
+
+@pytest.mark.parametrize("shape,scale", [((512, 128), 1.0), ((384, 96), 15.0), ((256, 64), 25.0), ((150, 61), 8.0)])
+def test_fused_dry_sweep_on_the_emulator_reproduces_the_oracle(emu, shape, scale):
+    """Slow, moderate (near back-trace in every direction) and fast flow (hand-over to the exact
+    path), wall blocks in the flow, TMA-staged and register-staged tiles, 64 x 28 tiles on ragged grids."""
+    w, h = shape
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=11)
+    base[1:, :, 0:2] *= np.float32(scale)
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        x0, y0 = int(rng.integers(0, w - 8)), int(rng.integers(4, h - 8))
+        wall[y0:y0 + 3, x0:x0 + 5, 0] = 1
+        wall[y0:y0 + 3, x0:x0 + 5, 1] = 0
+        base[y0:y0 + 3, x0:x0 + 5, 0:2] = 0.0
+    g = P.resolve_settings(None)
+    ora = make_oracle(g, base, water, wall, None)
+    em = EmuFused(emu, g, base, water, wall)
+    done = 0
+    for n in (1, 4):
+        ora.step_dry(n - done)
+        emu.ef_step_dry(em.h, n - done)
+        done = n
+        got, want = em.read(0, 0), ora.field(O.FIELD_BASE, 0)
+        assert np.array_equal(got, want), f"{shape} x{scale} after {n}: {(got != want).sum()} values differ, first at {np.argwhere(got != want)[0]}"
+    vmax = emu.ef_max_velocity(em.h)
+    assert (vmax > 1.0) == (scale >= 20.0)
+    em.close()
