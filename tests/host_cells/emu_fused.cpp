@@ -25,7 +25,7 @@ struct Field {
   }
 };
 struct Sim {
-  int W, H;
+  int W, H;  // W = columns of the local arrays (the pitch): the whole grid, or a strip with its ghost columns
   Geom g;
   DevParams dp;
   Field base[2], water[2], light[2];
@@ -121,17 +121,20 @@ void dry_iteration(Sim& s) {
 }  // namespace
 
 extern "C" {
-void* ef_create(int W, int H) {
+// one x-strip of a Wg-wide periodic grid: owned global columns [x_begin, x_begin + lw), `ghost` extra columns per
+// side (wsb_create with n_ranks > 1); ghost = 0 and lw = Wg is the single domain
+void* ef_create_strip(int Wg, int H, int x_begin, int lw, int ghost) {
   Sim* s = new Sim();
+  const int W = lw + 2 * ghost;
   s->W = W; s->H = H;
   const size_t n = (size_t)W * H;
   for (int k = 0; k < 2; k++) { s->base[k].alloc(n); s->water[k].alloc(n); s->light[k].alloc(n); s->wall[k].assign(n, 0); }
   s->fb.assign(n, make_float4(0.f, 0.f, 0.f, 0.f)); s->dep.assign(n, make_float2(0.f, 0.f));
   s->initial_T.assign(H + 2, 0.0f); s->sndT.assign(H + 2, 0.0f); s->sndW.assign(H + 2, 0.0f); s->sndV.assign(H + 2, 0.0f);
-  Geom& g = s->g;  // as wsb_create, single domain
-  g.Wg = W; g.H = H; g.pitch = W; g.gx0 = 0; g.wrap = 1; g.cx0 = 0; g.cx1 = W;
-  g.texelX = (float)(1.0 / (double)W); g.texelY = (float)(1.0 / (double)H);
-  g.Wf = (float)W; g.Hf = (float)H;
+  Geom& g = s->g;  // as wsb_create
+  g.Wg = Wg; g.H = H; g.pitch = W; g.gx0 = x_begin - ghost; g.wrap = ghost == 0 ? 1 : 0; g.cx0 = 0; g.cx1 = W;
+  g.texelX = (float)(1.0 / (double)Wg); g.texelY = (float)(1.0 / (double)H);
+  g.Wf = (float)Wg; g.Hf = (float)H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;
   g.cellHeightComp = 300.0f / g.Hf;
   g.nearV = 0.9f;
@@ -142,6 +145,7 @@ void* ef_create(int W, int H) {
   derived(*s);
   return s;
 }
+void* ef_create(int W, int H) { return ef_create_strip(W, H, 0, W, 0); }
 void ef_destroy(void* h) { delete (Sim*)h; }
 void ef_upload(void* h, const float* base, const float* water, const int8_t* wall) {
   Sim& s = *(Sim*)h;
@@ -166,6 +170,17 @@ void ef_set_profiles(void* h, const float* t0, const float* st, const float* sw,
 }
 void ef_set_iter(void* h, long long it) { Sim& s = *(Sim*)h; s.iter = it; derived(s); }
 int ef_uses_tma(void* h) { return ((Sim*)h)->use_tma ? 1 : 0; }
+// the 13 planes whose ghost columns csrc/wsb200.cu exchanges after an iteration: base_1, water_1, wall_1 and the
+// light texture just written (as 4-byte words)
+void ef_exchange_planes(void* h, void** out) {
+  Sim& s = *(Sim*)h;
+  const int dst = s.even ? 0 : 1;  // `even` has been toggled since the lighting half of k_fused_adv wrote it
+  int n = 0;
+  for (int k = 0; k < 4; k++) out[n++] = s.base[1].p.c[k];
+  for (int k = 0; k < 4; k++) out[n++] = s.water[1].p.c[k];
+  out[n++] = s.wall[1].data();
+  for (int k = 0; k < 4; k++) out[n++] = s.light[dst].p.c[k];
+}
 void ef_step(void* h, int n) { for (int i = 0; i < n; i++) fused_iteration(*(Sim*)h); }
 void ef_step_dry(void* h, int n) { for (int i = 0; i < n; i++) dry_iteration(*(Sim*)h); }
 float ef_max_velocity(void* h) { return __uint_as_float(((Sim*)h)->maxv); }

@@ -141,6 +141,9 @@ def emu():
     vp = ctypes.c_void_p
     L.ef_create.restype = vp
     L.ef_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ef_create_strip.restype = vp
+    L.ef_create_strip.argtypes = [ctypes.c_int] * 5
+    L.ef_exchange_planes.argtypes = [vp, ctypes.POINTER(vp)]
     L.ef_destroy.argtypes = [vp]
     L.ef_upload.argtypes = [vp, vp, vp, vp]
     L.ef_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
@@ -159,9 +162,11 @@ def emu():
 class EmuFused:
     """The FUSED schedule on the emulator, with the read-back views of wsb_read_rect."""
 
-    def __init__(self, L, g, base, water, wall, fi=None, profiles=None):
+    def __init__(self, L, g, base, water, wall, fi=None, profiles=None, strip=None):
+        """strip = (global width, first owned column, owned columns, ghost columns): base / water / wall are then
+        the strip's LOCAL arrays, ghost columns included (wsb_upload_local)."""
         self.L, (self.h_, self.w_) = L, base.shape[:2]
-        self.h = L.ef_create(self.w_, self.h_)
+        self.h = L.ef_create(self.w_, self.h_) if strip is None else L.ef_create_strip(strip[0], self.h_, strip[1], strip[2], strip[3])
         b, w, wl = (np.ascontiguousarray(a) for a in (base, water, wall))
         L.ef_upload(self.h, _ptr(b), _ptr(w), _ptr(wl))
         p = P.derive_params(g)
@@ -236,3 +241,46 @@ def test_fused_dry_sweep_on_the_emulator_reproduces_the_oracle(emu, shape, scale
     vmax = emu.ef_max_velocity(em.h)
     assert (vmax > 1.0) == (scale >= 20.0)
     em.close()
+
+
+@pytest.mark.parametrize("ranks,width", [(2, 256), (3, 336), (4, 512)])
+def test_strip_partition_on_the_emulator_is_bit_identical(emu, ranks, width):
+    """The multi-GPU plan of csrc/wsb200.cu (x-strips with 8 ghost columns per side, clamped instead of periodic
+    columns, one exchange of the 13 planes per iteration) executed with one emulated simulation per rank: every owned
+    cell must equal the oracle's single-domain run, for strip widths that are and are not multiples of the tile."""
+    h, ghost, iters = 64, 8, 6
+    g, base, water, wall, _ = stress_state(width, h, seed=23)
+    g["enablePrecipitation"] = False
+    ora = make_oracle(g, base, water, wall, None)
+    ora.step(iters)
+    bounds = [(r * width) // ranks for r in range(ranks + 1)]
+    sims = []
+    for r in range(ranks):
+        x0, lw = bounds[r], bounds[r + 1] - bounds[r]
+        cols = np.arange(x0 - ghost, x0 + lw + ghost) % width
+        sims.append(EmuFused(emu, g, base[:, cols], water[:, cols], wall[:, cols], strip=(width, x0, lw, ghost)))
+
+    def planes(sim):
+        ptrs = (ctypes.c_void_p * 13)()
+        emu.ef_exchange_planes(sim.h, ptrs)
+        return [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32)), shape=(h, sim.w_)) for p in ptrs]
+
+    for _ in range(iters):
+        for sim in sims:
+            emu.ef_step(sim.h, 1)
+        pl = [planes(sim) for sim in sims]
+        for r in range(ranks):
+            left, right = pl[(r - 1) % ranks], pl[(r + 1) % ranks]
+            lw_left = sims[(r - 1) % ranks].w_ - 2 * ghost
+            lw = sims[r].w_ - 2 * ghost
+            for k in range(13):
+                pl[r][k][:, :ghost] = left[k][:, lw_left:lw_left + ghost]    # the left neighbour's rightmost owned columns
+                pl[r][k][:, ghost + lw:] = right[k][:, ghost:2 * ghost]       # the right neighbour's leftmost owned columns
+    views = (("base", 0, 0, ora.field(O.FIELD_BASE, 0)), ("water1", 1, 1, ora.field(O.FIELD_WATER, 1)), ("wall", 2, 0, ora.field(O.FIELD_WALL, 0)),
+             ("light", 3, 2, ora.light_latest()))
+    for name, f, v, want in views:
+        got = np.concatenate([sim.read(f, v)[:, ghost:sim.w_ - ghost] for sim in sims], axis=1)
+        same = got == want
+        assert same.all(), f"{ranks} strips: {name} differs in {(~same).sum()} values, first at {np.argwhere(~same)[0]}"
+    for sim in sims:
+        sim.close()
