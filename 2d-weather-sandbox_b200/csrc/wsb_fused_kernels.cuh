@@ -750,8 +750,8 @@ constexpr size_t kSmem2 = (size_t)kPS2 * 4 * 12 + 16;
 // CLAMP_TO_EDGE rule, so the clamped row lighting_cell passes maps straight to a tile row)
 struct TileLightCtx {
   const float *sLS, *sLD, *sLU;
-  int X0, Y0;
-  __device__ __forceinline__ int si(int x, int y) const { return (y - Y0) * kSW2 + (x - X0); }
+  int origin;  // -(Y0 * kSW2 + X0): tile index of array cell (0, 0)
+  __device__ __forceinline__ int si(int x, int y) const { return y * kSW2 + x + origin; }
   __device__ __forceinline__ float lightS(int x, int y) const { return sLS[si(x, y)]; }
   __device__ __forceinline__ float lightIRdown(int x, int y) const { return sLD[si(x, y)]; }
   __device__ __forceinline__ float lightIRup(int x, int y) const { return sLU[si(x, y)]; }
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
     __syncthreads();
   }
 
-  const TileLightCtx lc{sLS, sLD, sLU, X0, Y0};
+  const TileLightCtx lc{sLS, sLD, sLU, -(Y0 * kSW2 + X0)};
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
   float vm = 0.0f;
@@ -922,9 +922,10 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       }
       if (!done) {
         adv_user_input(g, d, initial_T, texCoordX, texCoordY, aboveDist, wType, wDist, wVert, wVeg, base, water);
-        // idle frame: the wall texel passes through unchanged (in-range bytes need no saturation)
-        if (wType == w0.x && wDist == w0.y && wVeg == w0.w) wl = w0;
-        else wl = pack_wall(wType, wDist, wVert, wVeg);
+        // Only the wall tools (userInputType >= 10: distance 255, vegetation + 1) can push a component out of the
+        // RGBA8I range; every other frame the texel is re-assembled from in-range bytes without the saturation
+        if (d.in.userInputType >= 10) wl = pack_wall(wType, wDist, wVert, wVeg);
+        else wl = as_char4(pack_wall_in_range(wType, wDist, wVert, wVeg));
       }
       const size_t ci = (size_t)y * g.pitch + x;
       baseOut.st(ci, base);
@@ -934,7 +935,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       // lighting needs base_1's temperature of the cell BELOW a water-surface air cell
       // (lightingShader.frag:105), i.e. that cell's advection result
       float TBelow = 0.0f;
-      if (wl.y != 0 && wl.z == 1 && wl.x == WALLTYPE_WATER && fragCoordY < g.Hf - 1.0f) {
+      // air (DISTANCE != 0) one above (VERT_DISTANCE == 1) a WATER surface: one masked compare on the packed texel
+      const int wli = as_int(wl);
+      if ((wli & 0x00ff00ff) == ((1 << 16) | WALLTYPE_WATER) && (wli & 0xff00) != 0 && fragCoordY < g.Hf - 1.0f) {
         const int cb = c - SW;
         const char4 wb = as_char4(sWl[cb]);
         if (wb.y == 0) {  // the usual case: a wall cell, whose advection is a local update

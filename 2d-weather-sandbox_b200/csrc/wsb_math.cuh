@@ -104,6 +104,11 @@ __device__ __forceinline__ float wsb_cbrt(float m) {
   return y;
 }
 
+// the same texel as a packed word when every component is known to be in [-128, 127] already (no
+// wall tool is active: type, distance and vegetation only take values a texel held before)
+__device__ __forceinline__ int pack_wall_in_range(int t, int d, int v, int g) {
+  return (t & 0xff) | ((d & 0xff) << 8) | ((v & 0xff) << 16) | (g << 24);
+}
 // RGBA8I store, canonical saturation to [-128,127]
 __device__ __forceinline__ char4 pack_wall(int t, int d, int v, int g) {
   return make_char4((signed char)min(max(t, -128), 127), (signed char)min(max(d, -128), 127),
