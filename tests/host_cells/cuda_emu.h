@@ -129,6 +129,19 @@ static inline unsigned atomicMax(unsigned* p, unsigned v) {
   while (old < v && !a.compare_exchange_weak(old, v)) {}
   return old;
 }
+// static __shared__ variables: CTAs run one after the other, so one static object per declaration is "the CTA's"
+#undef __shared__
+#define __shared__ static
+// vector / integer atomics on global memory: one lock (the order of the adds is as unspecified as on the device)
+namespace emu { inline std::atomic_flag add_lock = ATOMIC_FLAG_INIT; }
+template <class F> static inline void emu_locked(F&& f) {
+  while (emu::add_lock.test_and_set(std::memory_order_acquire)) std::this_thread::yield();
+  f();
+  emu::add_lock.clear(std::memory_order_release);
+}
+static inline void atomicAdd(float4* p, float4 v) { emu_locked([&] { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }); }
+static inline void atomicAdd(float2* p, float2 v) { emu_locked([&] { p->x += v.x; p->y += v.y; }); }
+static inline int atomicAdd(int* p, int v) { int old = 0; emu_locked([&] { old = *p; *p += v; }); return old; }
 // full-warp collectives (the kernels only call them with every lane of the warp present)
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   emu::Warp& w = emu::tls.cta->warps[emu::tls.tid.x / 32];
@@ -140,3 +153,22 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
   return r;
 }
 static inline int __any_sync(unsigned, int pred) { return __reduce_max_sync(0xffffffffu, pred ? 1u : 0u) != 0u; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  emu::Warp& w = emu::tls.cta->warps[emu::tls.tid.x / 32];
+  memcpy(&w.slot[emu::tls.tid.x % 32], &v, 4);
+  w.bar.arrive_and_wait();
+  T r;
+  memcpy(&r, &w.slot[src & 31], 4);
+  w.bar.arrive_and_wait();
+  return r;
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  emu::Warp& w = emu::tls.cta->warps[emu::tls.tid.x / 32];
+  w.slot[emu::tls.tid.x % 32] = pred ? 1u : 0u;
+  w.bar.arrive_and_wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++) r |= w.slot[i] << i;
+  w.bar.arrive_and_wait();
+  return r;
+}

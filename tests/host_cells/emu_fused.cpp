@@ -13,6 +13,7 @@
 
 #define WSB_HOST_EMU 1
 #include "../../2d-weather-sandbox_b200/csrc/wsb_fused_kernels.cuh"
+#include "../../2d-weather-sandbox_b200/csrc/wsb_particles.cuh"
 
 using namespace wsb;
 
@@ -34,6 +35,10 @@ struct Sim {
   std::vector<float2> dep;
   std::vector<float> initial_T, sndT, sndW, sndV;
   unsigned maxv = 0;
+  std::vector<float> drops[2];
+  int ND = 0, last_drops = 0;
+  float lightning[4] = {0.f, 0.f, 0.f, 0.f}, inactive = 0.0f;
+  bool fb_dirty = false;
   bool even = true, pressure_pending = false, use_tma = false;
   long long iter = 0;
   long long launches = 0;
@@ -73,12 +78,13 @@ void fused_iteration(Sim& s) {
     maps.m[9] = map_of(s, s.light[0].p.c[0], kTX, kTY);
     maps.m[10] = map_of(s, s.light[0].p.c[1], kTX, kTY);
     const DevParams d = s.dp;
-    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0;
+    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = s.fb_dirty ? 1 : 0;
     emu::launch(tile_grid(s, kTY), kNT, kSmem1, [&] {
-      k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, 0, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
+      k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
                   s.wall[0].data());
     });
     s.launches++;
+    s.fb_dirty = false;  // the kernel has consumed the feedback and zeroed the texels that were hit (app.js:5933-5934 folded in)
   }
   {
     GlobalCtx c = ctx(s, 0, 0, 0, src);
@@ -101,6 +107,19 @@ void fused_iteration(Sim& s) {
   }
   s.even = !s.even;
   s.pressure_pending = true;
+  if (s.dp.p.enablePrecipitation && s.ND > 0) {  // csrc/wsb200.cu: precipitation()
+    const int psrc = s.even ? 1 : 0, pdst = s.even ? 0 : 1;  // chosen before the lighting block toggled `even`
+    derived(s);
+    const DevParams d = s.dp;
+    emu::launch(dim3((s.ND + 255) / 256, 1), 256, 0, [&] {
+      k_precipitation(s.drops[psrc].data(), s.drops[pdst].data(), s.base[1].p, s.water[1].p, s.fb.data(), s.dep.data(), s.lightning,
+                      &s.inactive, s.g, d, s.ND);
+    });
+    s.fb_dirty = true;
+    s.last_drops = pdst;
+    emu::launch(dim3(1, 1), 32, 0, [&] { k_latch(s.fb.data(), &s.inactive, s.lightning, d.iterNum, (s.iter % 600 == 0) ? 1 : 0); });
+    s.launches += 2;
+  }
   s.iter++;
 }
 // csrc/wsb200.cu: dry_iteration, FUSED schedule
@@ -158,6 +177,23 @@ void ef_upload(void* h, const float* base, const float* water, const int8_t* wal
   s.even = true; s.iter = 0; s.pressure_pending = false; s.maxv = 0;
   derived(s);
 }
+void ef_upload_drops(void* h, const float* drops, int nd) {
+  Sim& s = *(Sim*)h;
+  s.ND = nd;
+  for (int k = 0; k < 2; k++) s.drops[k].assign(drops, drops + (size_t)nd * 5);
+  s.last_drops = 0; s.inactive = 0.0f; s.fb_dirty = false;
+  memset(s.lightning, 0, sizeof(s.lightning));
+  std::fill(s.fb.begin(), s.fb.end(), make_float4(0.f, 0.f, 0.f, 0.f));
+  std::fill(s.dep.begin(), s.dep.end(), make_float2(0.f, 0.f));
+}
+void ef_read_drops(void* h, float* dst) { Sim& s = *(Sim*)h; memcpy(dst, s.drops[s.last_drops].data(), (size_t)s.ND * 5 * 4); }
+void ef_read_feedback(void* h, float* fb, float* dep) {
+  Sim& s = *(Sim*)h;
+  memcpy(fb, s.fb.data(), s.fb.size() * sizeof(float4));
+  memcpy(dep, s.dep.data(), s.dep.size() * sizeof(float2));
+}
+void ef_get_latches(void* h, float* lightning4, float* inactive) { Sim& s = *(Sim*)h; memcpy(lightning4, s.lightning, 16); *inactive = s.inactive; }
+void ef_set_inactive(void* h, float v) { ((Sim*)h)->inactive = v; }
 void ef_set_params(void* h, const wsb_params* p) { ((Sim*)h)->dp.p = *p; }
 void ef_set_frame_inputs(void* h, const wsb_frame_inputs* in) { Sim& s = *(Sim*)h; s.dp.in = *in; derived(s); }
 void ef_set_profiles(void* h, const float* t0, const float* st, const float* sw, const float* sv) {

@@ -156,6 +156,11 @@ def emu():
     L.ef_max_velocity.argtypes = [vp]
     L.ef_max_velocity.restype = ctypes.c_float
     L.ef_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    L.ef_upload_drops.argtypes = [vp, vp, ctypes.c_int]
+    L.ef_read_drops.argtypes = [vp, vp]
+    L.ef_read_feedback.argtypes = [vp, vp, vp]
+    L.ef_get_latches.argtypes = [vp, vp, vp]
+    L.ef_set_inactive.argtypes = [vp, ctypes.c_float]
     return L
 
 
@@ -317,3 +322,52 @@ def test_strip_partition_on_the_emulator_is_bit_identical(emu, ranks, width):
         assert same.all(), f"{ranks} strips: {name} differs in {(~same).sum()} values, first at {np.argwhere(~same)[0]}"
     for sim in sims:
         sim.close()
+
+
+def test_particle_pass_on_the_emulator(emu):
+    """k_precipitation (warp-cooperative sprite rasterisation with vector atomics, inactive count per CTA) and
+    k_latch on the emulator: droplet records bit-exact after the first pass, the additive feedback / deposition
+    textures equal up to fp32 summation order, the fields within the north-star tolerance after several iterations
+    (the same bars as tests/test_gpu_parity.py)."""
+    w, h = 128, 64
+    g, base, water, wall, drops = stress_state(w, h, seed=3)
+    drops = np.ascontiguousarray(drops[:700])
+    g["enablePrecipitation"] = True
+    air = wall[..., 1] != 0
+    water[h // 2:, :, 1] += np.where(air[h // 2:], np.float32(20.0), np.float32(0.0))  # spawning becomes likely
+    water[h // 2:, :, 0] += np.where(air[h // 2:], np.float32(20.0), np.float32(0.0))
+    ora = make_oracle(g, base, water, wall, drops)
+    em = EmuFused(emu, g, base, water, wall)
+    emu.ef_upload_drops(em.h, _ptr(drops), drops.shape[0])
+    ora.inactive_droplets = 5.0
+    emu.ef_set_inactive(em.h, 5.0)
+
+    def state():
+        d = np.empty_like(drops)
+        emu.ef_read_drops(em.h, _ptr(d))
+        fb, dep = np.empty((h, w, 4), np.float32), np.empty((h, w, 2), np.float32)
+        emu.ef_read_feedback(em.h, _ptr(fb), _ptr(dep))
+        return d, fb, dep
+
+    ora.step(1)
+    emu.ef_step(em.h, 1)
+    d, fb, dep = state()
+    assert np.array_equal(d, ora.droplets()), "droplet records after the first pass"
+    assert np.allclose(fb, ora.field(O.FIELD_FEEDBACK), rtol=1e-5, atol=1e-6)
+    assert np.allclose(dep, ora.field(O.FIELD_DEPOSITION), rtol=1e-5, atol=1e-6)
+    assert (d[:, 2] >= 0).sum() > 50 and fb[0, 0, 0] > 0  # active droplets and the inactive count
+    ora.step(5)
+    emu.ef_step(em.h, 5)
+    d, fb, dep = state()
+    want = ora.droplets()
+    assert np.array_equal(d[:, 2] < 0, want[:, 2] < 0)  # the same droplets are active
+    assert np.allclose(d, want, rtol=1e-4, atol=1e-6)
+    for name, f, v, of, ob in (("base", 0, 0, O.FIELD_BASE, 0), ("water1", 1, 1, O.FIELD_WATER, 1)):
+        got, ref = em.read(f, v).astype(np.float64), ora.field(of, ob).astype(np.float64)
+        err = np.max(np.abs(got - ref) / (np.abs(ref) + 1e-3))
+        assert err < 1e-5, f"{name}: relative error {err:.3g} after 6 iterations with particles"
+    assert np.array_equal(em.read(2, 0), ora.field(O.FIELD_WALL, 0))
+    lightning, inactive = np.zeros(4, np.float32), ctypes.c_float()
+    emu.ef_get_latches(em.h, _ptr(lightning), ctypes.byref(inactive))
+    assert np.array_equal(lightning, ora.lightning) and inactive.value == ora.inactive_droplets
+    em.close()
