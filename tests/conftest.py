@@ -1,3 +1,4 @@
+import ctypes
 import os
 import subprocess
 import sys
@@ -8,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+HOST_CELLS = os.path.join(ROOT, "tests", "host_cells")
 
 
 def pytest_configure(config):
@@ -35,3 +37,62 @@ def save100():
     import wsb200
 
     return wsb200.savefile.load(os.path.join(GOLDEN, "100x100_test.weathersandbox"))
+
+
+# ---- test infrastructure built from the product's own sources (tests/host_cells/) ----------------
+@pytest.fixture(scope="session")
+def lib():
+    subprocess.check_call(["make", "-C", HOST_CELLS, "-s"])
+    L = ctypes.CDLL(os.path.join(HOST_CELLS, "libhostcells.so"))
+    import wsb200
+
+    P = wsb200.params
+    vp = ctypes.c_void_p
+    L.hc_create.restype = vp
+    L.hc_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.hc_destroy.argtypes = [vp]
+    L.hc_upload.argtypes = [vp, vp, vp, vp]
+    L.hc_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
+    L.hc_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
+    L.hc_set_profiles.argtypes = [vp, vp, vp, vp, vp]
+    L.hc_set_iter.argtypes = [vp, ctypes.c_longlong]
+    L.hc_set_feedback.argtypes = [vp, vp, vp]
+    L.hc_run_pass.argtypes = [vp, ctypes.c_int]
+    L.hc_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    return L
+
+
+
+@pytest.fixture(scope="session")
+def emu():
+    subprocess.check_call(["make", "-C", HOST_CELLS, "-s", "libemufused.so"])
+    L = ctypes.CDLL(os.path.join(HOST_CELLS, "libemufused.so"))
+    import wsb200
+
+    P = wsb200.params
+    vp = ctypes.c_void_p
+    L.ef_create.restype = vp
+    L.ef_create.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.ef_create_strip.restype = vp
+    L.ef_create_strip.argtypes = [ctypes.c_int] * 5
+    L.ef_exchange_planes.argtypes = [vp, ctypes.POINTER(vp)]
+    L.ef_destroy.argtypes = [vp]
+    L.ef_upload.argtypes = [vp, vp, vp, vp]
+    L.ef_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
+    L.ef_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
+    L.ef_set_profiles.argtypes = [vp, vp, vp, vp, vp]
+    L.ef_set_iter.argtypes = [vp, ctypes.c_longlong]
+    L.ef_uses_tma.argtypes = [vp]
+    L.ef_step.argtypes = [vp, ctypes.c_int]
+    L.ef_step_dry.argtypes = [vp, ctypes.c_int]
+    L.ef_max_velocity.argtypes = [vp]
+    L.ef_max_velocity.restype = ctypes.c_float
+    L.ef_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
+    L.ef_upload_drops.argtypes = [vp, vp, ctypes.c_int]
+    L.ef_read_drops.argtypes = [vp, vp]
+    L.ef_read_feedback.argtypes = [vp, vp, vp]
+    L.ef_get_latches.argtypes = [vp, vp, vp]
+    L.ef_set_inactive.argtypes = [vp, ctypes.c_float]
+    return L
+
+

@@ -20,25 +20,6 @@ P = wsb200.params
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_cells")
 
 
-@pytest.fixture(scope="module")
-def lib():
-    subprocess.check_call(["make", "-C", HERE, "-s"])
-    L = ctypes.CDLL(os.path.join(HERE, "libhostcells.so"))
-    vp = ctypes.c_void_p
-    L.hc_create.restype = vp
-    L.hc_create.argtypes = [ctypes.c_int, ctypes.c_int]
-    L.hc_destroy.argtypes = [vp]
-    L.hc_upload.argtypes = [vp, vp, vp, vp]
-    L.hc_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
-    L.hc_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
-    L.hc_set_profiles.argtypes = [vp, vp, vp, vp, vp]
-    L.hc_set_iter.argtypes = [vp, ctypes.c_longlong]
-    L.hc_set_feedback.argtypes = [vp, vp, vp]
-    L.hc_run_pass.argtypes = [vp, ctypes.c_int]
-    L.hc_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
-    return L
-
-
 def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -134,36 +115,6 @@ def test_cell_headers_user_input_and_slow_processes(lib):
 # ---------------------------------------------------------------------------------------------
 # the fused kernels themselves, on a host emulation of the CUDA execution model
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def emu():
-    subprocess.check_call(["make", "-C", HERE, "-s", "libemufused.so"])
-    L = ctypes.CDLL(os.path.join(HERE, "libemufused.so"))
-    vp = ctypes.c_void_p
-    L.ef_create.restype = vp
-    L.ef_create.argtypes = [ctypes.c_int, ctypes.c_int]
-    L.ef_create_strip.restype = vp
-    L.ef_create_strip.argtypes = [ctypes.c_int] * 5
-    L.ef_exchange_planes.argtypes = [vp, ctypes.POINTER(vp)]
-    L.ef_destroy.argtypes = [vp]
-    L.ef_upload.argtypes = [vp, vp, vp, vp]
-    L.ef_set_params.argtypes = [vp, ctypes.POINTER(P.WsbParams)]
-    L.ef_set_frame_inputs.argtypes = [vp, ctypes.POINTER(P.WsbFrameInputs)]
-    L.ef_set_profiles.argtypes = [vp, vp, vp, vp, vp]
-    L.ef_set_iter.argtypes = [vp, ctypes.c_longlong]
-    L.ef_uses_tma.argtypes = [vp]
-    L.ef_step.argtypes = [vp, ctypes.c_int]
-    L.ef_step_dry.argtypes = [vp, ctypes.c_int]
-    L.ef_max_velocity.argtypes = [vp]
-    L.ef_max_velocity.restype = ctypes.c_float
-    L.ef_read.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp]
-    L.ef_upload_drops.argtypes = [vp, vp, ctypes.c_int]
-    L.ef_read_drops.argtypes = [vp, vp]
-    L.ef_read_feedback.argtypes = [vp, vp, vp]
-    L.ef_get_latches.argtypes = [vp, vp, vp]
-    L.ef_set_inactive.argtypes = [vp, ctypes.c_float]
-    return L
-
-
 class EmuFused:
     """The FUSED schedule on the emulator, with the read-back views of wsb_read_rect."""
 
