@@ -79,11 +79,26 @@ void fused_iteration(Sim& s) {
     maps.m[10] = map_of(s, s.light[0].p.c[1], kTX, kTY);
     const DevParams d = s.dp;
     const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = s.fb_dirty ? 1 : 0;
-    emu::launch(tile_grid(s, kTY), kNT, kSmem1, [&] {
-      k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
-                  s.wall[0].data());
-    });
-    s.launches++;
+    auto launch_pvb = [&](int cx0, int cx1) {
+      c.g.cx0 = cx0;
+      c.g.cx1 = cx1;
+      emu::launch(dim3((cx1 - cx0 + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem1, [&] {
+        k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
+                    s.wall[0].data());
+      });
+      s.launches++;
+    };
+    // a strip launches the tiles clear of the ghost columns first and the two edge tile columns after the ghost
+    // exchange has landed (csrc/wsb200.cu); the exchange itself is done by the test between iterations
+    const int kGhostCols = 8;
+    const int innerEnd = kTX + ((s.W - (kGhostCols + kHX) - kTX) / kTX) * kTX;
+    if (!s.g.wrap && s.pressure_pending && innerEnd > kTX) {
+      launch_pvb(kTX, innerEnd);
+      launch_pvb(0, kTX);
+      launch_pvb(innerEnd, s.W);
+    } else {
+      launch_pvb(0, s.W);
+    }
     s.fb_dirty = false;  // the kernel has consumed the feedback and zeroed the texels that were hit (app.js:5933-5934 folded in)
   }
   {
