@@ -63,10 +63,10 @@ def lib():
 
 
 
-@pytest.fixture(scope="session")
-def emu():
-    subprocess.check_call(["make", "-C", HOST_CELLS, "-s", "libemufused.so"])
-    L = ctypes.CDLL(os.path.join(HOST_CELLS, "libemufused.so"))
+def _load_emu(name="libemufused.so", flags=None):
+    cmd = ["make", "-C", HOST_CELLS, "-s", name] + ([f"EMU_FLAGS={flags}"] if flags else [])
+    subprocess.check_call(cmd)
+    L = ctypes.CDLL(os.path.join(HOST_CELLS, name))
     import wsb200
 
     P = wsb200.params
@@ -96,3 +96,12 @@ def emu():
     return L
 
 
+@pytest.fixture(scope="session")
+def emu():
+    return _load_emu()
+
+
+@pytest.fixture(scope="session")
+def emu_pairadv():
+    """The experimental WSB_DRY_PAIRADV variant of k_fused_dry (two cells per thread in the advection phase)."""
+    return _load_emu("libemufused_pairadv.so", "-DWSB_DRY_PAIRADV=1")
