@@ -325,3 +325,25 @@ def test_particle_pass_on_the_emulator(emu):
     emu.ef_get_latches(em.h, _ptr(lightning), ctypes.byref(inactive))
     assert np.array_equal(lightning, ora.lightning) and inactive.value == ora.inactive_droplets
     em.close()
+
+
+def test_fused_kernels_on_the_emulator_forcing_and_slow_processes(emu):
+    """Global drying / heating / sounding forcing (the uniform-rate blocks the kernels skip when a rate is exactly 0)
+    and the processes that run at multiples of 20, 100 and 600 iterations, on the fused kernels."""
+    w, h = 192, 64
+    g, base, water, wall, _ = stress_state(w, h, seed=13)
+    g["enablePrecipitation"] = False
+    rng = np.random.default_rng(13)
+    prof = (P.initial_T_profile(h, g), (300 + rng.uniform(-5, 5, h + 1)).astype(np.float32), rng.uniform(0, 20, h + 1).astype(np.float32),
+            rng.uniform(-0.2, 0.2, h + 1).astype(np.float32))
+    for drying, heating, forcing, it0 in ((0.00002, 0.0003, 0.95, 97), (0.0, 0.0003, 0.0, 598), (0.00002, 0.0, 0.5, 18)):
+        g["globalDrying"], g["globalHeating"], g["soundingForcing"] = drying, heating, forcing
+        ora = make_oracle(g, base, water, wall, None)
+        ora.set_profiles(*prof)
+        em = EmuFused(emu, g, base, water, wall, profiles=prof)
+        ora.iter = it0
+        emu.ef_set_iter(em.h, it0)
+        ora.step(5)
+        emu.ef_step(em.h, 5)
+        _compare_fused(em, ora, f"forcing ({drying}, {heating}, {forcing}) from iteration {it0}")
+        em.close()
