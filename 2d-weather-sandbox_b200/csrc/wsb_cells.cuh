@@ -377,7 +377,10 @@ __device__ void boundary_cell(const C& c, const Geom& g, const DevParams& d, con
             water.z += (avgNeighborSoilMoisture - water.z) * 0.02f;
           }
           int vegetationGrowthRate = (int)(water.z * sqrtf(lightAbove.x) * 0.01f);
-          if (vegetationGrowthRate > 0 && d.iterI % ((100 / vegetationGrowthRate) * 100) == 0) {
+          // growth rates above 100 make the reference's interval (100 / rate) * 100 zero and its `%` undefined
+          // (GLSL ES 3.00 5.9); frozen as "no growth tick" (DESIGN 2), identically in the oracle
+          const int growthInterval = vegetationGrowthRate > 0 ? (100 / vegetationGrowthRate) * 100 : 0;
+          if (growthInterval > 0 && d.iterI % growthInterval == 0) {
             if ((int)map_rangeC(realTempAboveSurface, CtoK(0.0f), CtoK(25.0f), 0.0f, 127.0f) > wVeg) wVeg += 1;
           }
           int subInterval = d.iterI / 100;

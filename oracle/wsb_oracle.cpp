@@ -534,7 +534,9 @@ void pass_boundary(Sim& s) {
                 water[SOIL_MOISTURE] += (avgNeighborSoilMoisture - water[SOIL_MOISTURE]) * moistureSmoothingRate;
               }
               int vegetationGrowthRate = (int)(water[SOIL_MOISTURE] * sqrtf(lightAboveSurface[SUNLIGHT]) * 0.01f);  // :460
-              if (vegetationGrowthRate > 0 && iterI % ((100 / vegetationGrowthRate) * 100) == 0) {
+              // rate > 100: the interval is 0 and `% 0` is undefined in GLSL ES 3.00 (5.9) — frozen as "no growth tick" 
+              const int growthInterval = vegetationGrowthRate > 0 ? (100 / vegetationGrowthRate) * 100 : 0;
+              if (growthInterval > 0 && iterI % growthInterval == 0) {
                 if ((int)map_rangeC(realTempAboveSurface, CtoK(0.0f), CtoK(25.0f), 0.0f, 127.0f) > wall[VEGETATION]) wall[VEGETATION] += 1;
               }
               int subInterval = iterI / 100;  // :467

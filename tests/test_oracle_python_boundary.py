@@ -280,7 +280,8 @@ def boundary(base1, water1, wall1, vort, light0, fb, dep, p, fi, initial_t, iter
                                 water[SNOW] = water[SNOW] + (tot_snow / num - water[SNOW]) * f32(0.02)
                                 water[SOIL_MOISTURE] = water[SOIL_MOISTURE] + (tot_soil / num - water[SOIL_MOISTURE]) * f32(0.02)
                             growth = int(water[SOIL_MOISTURE] * np.sqrt(light_above[SUNLIGHT]) * f32(0.01))
-                            if growth > 0 and it_i % ((100 // growth) * 100) == 0:
+                            interval = (100 // growth) * 100 if growth > 0 else 0  # rate > 100: `% 0`, frozen as "no tick"
+                            if interval > 0 and it_i % interval == 0:
                                 if int(map_range_c(real_above, c_to_k(Z), c_to_k(f32(25.0)), Z, f32(127.0))) > wall[VEGETATION]:
                                     wall[VEGETATION] += 1
                             sub = it_i // 100
@@ -321,10 +322,17 @@ def boundary(base1, water1, wall1, vort, light0, fb, dep, p, fi, initial_t, iter
     return out_b, out_w, out_wl
 
 
-@pytest.mark.parametrize("iter_num", [0, 7, 40, 300])
-def test_boundary_pass_matches_python_transliteration(iter_num):
+# wet=True: soil moisture 250 .. 900 under a high sun pushes vegetationGrowthRate past 100, where the
+# reference's growth interval (100 / rate) * 100 is 0 and its `%` undefined (boundaryShader.frag:460-462;
+# two shipped saves hold such cells).  Frozen as "no growth tick" in the kernels, the oracle and here.
+@pytest.mark.parametrize("iter_num,wet", [(0, False), (7, False), (40, False), (300, False), (300, True), (1000, True)])
+def test_boundary_pass_matches_python_transliteration(iter_num, wet):
     w, h = 96, 40
     g, base, water, wall, _ = stress_state(w, h, seed=17)
+    if wet:
+        g["sunAngle"] = 85.0
+        land = (wall[..., 1] == 0) & np.isin(wall[..., 0], (1, 3, 4, 6))  # LAND, FIRE, URBAN, INDUSTRIAL fall through to :460
+        water[..., 2] = np.where(land, f32(250.0) + f32(650.0) * np.random.default_rng(5).random((h, w)).astype(f32), water[..., 2])
     g["enablePrecipitation"] = False
     p = P.derive_params(g)
     fi = P.frame_inputs(g)
@@ -339,11 +347,17 @@ def test_boundary_pass_matches_python_transliteration(iter_num):
     fb[...] = np.where(hit[..., None], rng.normal(0, 0.05, (h, w, 4)), 0).astype(f32)
     fb[..., 0] = np.abs(fb[..., 0]) * 10
     dep[...] = np.where(hit[..., None], rng.uniform(0, 2, (h, w, 2)), 0).astype(f32)
+    if wet:  # sunlight travels one row per iteration and has not reached the surface yet: put it there
+        ora.field(O.FIELD_LIGHT, 0, copy=False)[..., 0] = f32(900.0)
     ora.run_pass(0)  # velocity -> frameBuff_1
     ora.run_pass(1)  # curl
     ora.run_pass(2)  # vorticity force
     args = (ora.field(O.FIELD_BASE, 1), ora.field(O.FIELD_WATER, 1), ora.field(O.FIELD_WALL, 1), ora.field(O.FIELD_VORT),
             ora.field(O.FIELD_LIGHT, 0), fb.copy(), dep.copy(), p, fi, initial_t, iter_num)
+    if wet:  # the branch under test must actually be reached
+        surf = (args[2][..., 1] == 0) & (np.roll(args[2][..., 1], -1, axis=0) != 0) & np.isin(args[2][..., 0], (1, 3, 4, 6))
+        above = np.roll(args[4][..., 0], -1, axis=0)
+        assert ((args[1][..., 2] * np.sqrt(above) * f32(0.01))[surf] > 100).sum() > 10
     want_b, want_w, want_wl = boundary(*args)
     ora.run_pass(3)
     got_b, got_w, got_wl = ora.field(O.FIELD_BASE, 0), ora.field(O.FIELD_WATER, 0), ora.field(O.FIELD_WALL, 0)
