@@ -21,6 +21,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <new>
@@ -133,6 +134,108 @@ __global__ void k_unpack_halo(HaloPlanes hp, int pitch, int H, int lw, const int
   f[(size_t)y * pitch + kGhost + lw + i] = fromRight[t];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory ghost exchange (default transport): every rank allocates the exchanged planes in ONE
+// arena and hands its neighbours an IPC handle to it (wsb_peer_info / wsb_connect_peers).  After the
+// edge tiles of an iteration's advection kernel, k_push_ghosts stores this rank's outermost owned
+// columns STRAIGHT into the neighbours' ghost columns over NVLink — no staging buffers, no unpack —
+// and raises a sequence flag in the neighbour's arena; k_wait_ghosts (one thread, ahead of the next
+// boundary kernel's edge tiles) waits for both neighbours' flags.  Flags (one 128-byte line each):
+//   kFlagDataL / kFlagDataR   written by the left / right neighbour: "your ghost zone holds exchange #seq"
+//   kFlagFreeL / kFlagFreeR   written by the left / right neighbour: "I have finished reading the ghost
+//                             columns you filled in exchange #seq-1 (you may overwrite them)" — a rank's
+//                             ghost columns are plain columns of its ping-pong planes, not a double buffer
+//   kFlagBlocks               last-block-done counter of k_push_ghosts;  kFlagErr  a spin ran out
+// Every wait is bounded (kSpinLimitNs): a missing neighbour becomes an error from wsb_sync, not a hang.
+// ---------------------------------------------------------------------------------------------
+enum { kFlagDataL = 0, kFlagDataR, kFlagFreeL, kFlagFreeR, kFlagBlocks, kFlagErr, kNumFlags };
+constexpr int kFlagStride = 32;  // unsigned words: one 128-byte line per flag
+constexpr unsigned long long kSpinLimitNs = 20ull * 1000 * 1000 * 1000;  // default; WSB_SPIN_LIMIT_MS overrides (tests)
+constexpr int kArenaSlots = 21;  // base_0 x4 | base_1 x4 | water_1 x4 | wall_1 | light_0 x4 | light_1 x4
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= seq (sequence numbers wrap: compare as a signed difference)
+__device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned seq, unsigned* err, unsigned long long limitNs) {
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+    if (global_ns() - t0 > limitNs) { atomicExch(err, 1u); return; }
+    __nanosleep(100);
+  }
+}
+
+struct PushArgs {
+  unsigned char *mine, *left, *right;   // arenas: this rank's, the neighbours' (peer-mapped)
+  unsigned long long pbMine, pbLeft, pbRight;  // bytes per plane slot
+  int pitchMine, pitchLeft, pitchRight;
+  int lw, lwLeft, H, vec;
+  int n;                                // planes to exchange
+  int slot[13];
+  unsigned seq;
+  unsigned long long spinNs;
+};
+__device__ __forceinline__ unsigned* flag_of(unsigned char* arena, unsigned long long pb, int f) {
+  return reinterpret_cast<unsigned*>(arena + pb * kArenaSlots) + f * kFlagStride;
+}
+
+__global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ PushArgs a) {
+  unsigned* myFlags = flag_of(a.mine, a.pbMine, 0);
+  if (threadIdx.x == 0) {
+    // everything of this rank that reads the ghost columns of exchange seq-1 precedes this kernel in stream order
+    st_release_sys(flag_of(a.left, a.pbLeft, kFlagFreeR), a.seq);
+    st_release_sys(flag_of(a.right, a.pbRight, kFlagFreeL), a.seq);
+    wait_flag(myFlags + kFlagFreeL * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
+    wait_flag(myFlags + kFlagFreeR * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = a.H * 2;  // (row, column quad)
+  if (t < per * a.n) {
+    const int k = t / per, r = t - k * per;
+    const int y = r >> 1, q = (r & 1) * 4;
+    const unsigned long long sl = (unsigned long long)a.slot[k];
+    const int* src = reinterpret_cast<const int*>(a.mine + sl * a.pbMine) + (size_t)y * a.pitchMine;
+    int* dl = reinterpret_cast<int*>(a.left + sl * a.pbLeft) + (size_t)y * a.pitchLeft + kGhost + a.lwLeft + q;  // its right ghost zone
+    int* dr = reinterpret_cast<int*>(a.right + sl * a.pbRight) + (size_t)y * a.pitchRight + q;                   // its left ghost zone
+    const int* sL = src + kGhost + q;   // my leftmost owned columns
+    const int* sR = src + a.lw + q;     // my rightmost owned columns
+    if (a.vec) {
+      *reinterpret_cast<int4*>(dl) = *reinterpret_cast<const int4*>(sL);
+      *reinterpret_cast<int4*>(dr) = *reinterpret_cast<const int4*>(sR);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { dl[i] = sL[i]; dr[i] = sR[i]; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned* done = myFlags + kFlagBlocks * kFlagStride;
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {  // last block: every block's stores are visible system-wide
+      *done = 0u;
+      __threadfence_system();
+      st_release_sys(flag_of(a.left, a.pbLeft, kFlagDataR), a.seq);
+      st_release_sys(flag_of(a.right, a.pbRight, kFlagDataL), a.seq);
+    }
+  }
+}
+
+__global__ void k_wait_ghosts(unsigned* myFlags, unsigned seq, unsigned long long spinNs) {
+  wait_flag(myFlags + kFlagDataL * kFlagStride, seq, myFlags + kFlagErr * kFlagStride, spinNs);
+  wait_flag(myFlags + kFlagDataR * kFlagStride, seq, myFlags + kFlagErr * kFlagStride, spinNs);
+}
+
 // n scattered texels of one RGBA32F field -> dense float4 array (weather-station style probes);
 // applyPressure: the field is the fused schedule's base_1 with the pressure pass still pending
 __global__ void k_gather_points(GlobalCtx c, Planes4 field, int applyPressure, int n, const int* __restrict__ xy, int lx_off,
@@ -140,7 +243,7 @@ __global__ void k_gather_points(GlobalCtx c, Planes4 field, int applyPressure, i
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int x = xy[2 * i] + lx_off, y = xy[2 * i + 1];
-  if (x < 0 || x >= c.g.pitch || y < 0 || y >= c.g.H) {  // not in this rank's strip
+  if (x < c.g.ox0 || x >= c.g.ox1 || y < 0 || y >= c.g.H) {  // not one of this rank's own columns (ghost columns belong to the neighbour)
     out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
@@ -172,7 +275,7 @@ struct wsb_sim {
 
   // one RGBA32F texture = four float planes, with the TMA descriptors of each plane for the two
   // box shapes the fused kernels stage (tile + 2-cell halo: dry / advection; tile + 3: boundary)
-  struct Field { Planes4 p; CUtensorMap map2[4], map3[4], map0[4], mapD[4]; };  // map0: the bare tile (own-cell operands); mapD: dry-sweep box
+  struct Field { Planes4 p; CUtensorMap map2[4], map3[4], map0[4], mapD[4]; int slot = -1; };  // map0: the bare tile (own-cell operands); mapD: dry-sweep box; slot: first exchange-arena slot (strips)
   Field base[2] = {}, water[2] = {}, light[2] = {};
   int* wall[2] = {};
   CUtensorMap wallMap2[2], wallMap3[2], wallMapD[2];
@@ -210,6 +313,20 @@ struct wsb_sim {
   void* comm = nullptr;
   unsigned char *sendL = nullptr, *sendR = nullptr, *recvL = nullptr, *recvR = nullptr;
   size_t halo_bytes = 0;
+  // peer-memory transport (strips): the exchanged planes live in one arena the neighbours map
+  unsigned char* arena = nullptr;
+  size_t plane_bytes = 0, arena_bytes = 0;
+  int wall_slot[2] = {-1, -1};
+  bool peer_mode = false;                   // wsb_connect_peers succeeded: k_push_ghosts / k_wait_ghosts instead of NCCL
+  unsigned char *peerL = nullptr, *peerR = nullptr;
+  bool peerL_ipc = false, peerR_ipc = false;  // opened with cudaIpcOpenMemHandle (to be closed)
+  size_t pbL = 0, pbR = 0;
+  int pitchL = 0, pitchR = 0, lwL = 0;
+  unsigned xseq = 0, pending_seq = 0;       // exchanges issued / the one in flight
+  unsigned long long spin_ns = kSpinLimitNs;
+  cudaEvent_t evEdge = nullptr, evPush = nullptr;
+  bool push_pending = false;                // a k_push_ghosts is reading this rank's edge columns
+  int pvbInnerEnd = 0, advEdgeStart = 0;    // tile-column split of the strip (local columns)
 };
 
 namespace {
@@ -268,17 +385,55 @@ struct ProfScope {  // brackets the launches of one kernel class on one stream
 };
 
 // --- halo exchange ---------------------------------------------------------------------------
-void add_planes(HaloPlanes& hp, const Planes4& f) {
-  for (int k = 0; k < 4; k++) hp.p[hp.n++] = reinterpret_cast<int*>(f.c[k]);
+// The planes one exchange carries: pointers for the NCCL transport, arena slots for the peer transport
+struct XPlanes { HaloPlanes hp{}; int slot[kMaxHaloPlanes]; };
+void add_planes(XPlanes& x, const wsb_sim::Field& f) {
+  for (int k = 0; k < 4; k++) {
+    x.slot[x.hp.n] = f.slot + k;
+    x.hp.p[x.hp.n++] = reinterpret_cast<int*>(f.p.c[k]);
+  }
 }
-// Ghost-column exchange on comm_stream, ordered after everything enqueued on the compute stream
-// so far.  It stays in flight (exch_pending) until join_exchange() makes the compute stream wait
-// for it — the next iteration's interior tiles run beside it.
-int exchange(wsb_sim* s, const HaloPlanes& hp) {
+void add_wall(XPlanes& x, const wsb_sim* s, int k) {
+  x.slot[x.hp.n] = s->wall_slot[k];
+  x.hp.p[x.hp.n++] = s->wall[k];
+}
+
+// Ghost-column exchange on comm_stream.  It starts once `after` (an event on the compute stream:
+// the iteration's edge tiles, or everything enqueued so far) has fired and stays in flight
+// (exch_pending) until join_exchange() orders the compute stream behind it — the interior tiles
+// of the advection kernel and of the next iteration's boundary kernel run beside it.
+int exchange(wsb_sim* s, const XPlanes& xp, bool afterEdge) {
   if (s->cfg.n_ranks <= 1) return 0;
   cudaStream_t cs = s->comm_stream;
-  CK(cudaEventRecord(s->evCompute, s->stream));
-  CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
+  const HaloPlanes& hp = xp.hp;
+  if (afterEdge) {
+    CK(cudaStreamWaitEvent(cs, s->evEdge, 0));
+  } else {
+    CK(cudaEventRecord(s->evCompute, s->stream));
+    CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
+  }
+  if (s->peer_mode) {
+    ProfScope prof(s, WSB_KERNEL_HALO, cs);
+    PushArgs a{};
+    a.mine = s->arena; a.left = s->peerL; a.right = s->peerR;
+    a.pbMine = s->plane_bytes; a.pbLeft = s->pbL; a.pbRight = s->pbR;
+    a.pitchMine = s->pitch; a.pitchLeft = s->pitchL; a.pitchRight = s->pitchR;
+    a.lw = s->lw; a.lwLeft = s->lwL; a.H = s->H;
+    a.vec = (s->pitch % 4 == 0 && s->pitchL % 4 == 0 && s->pitchR % 4 == 0 && s->lw % 4 == 0 && s->lwL % 4 == 0) ? 1 : 0;
+    a.n = hp.n;
+    for (int k = 0; k < hp.n; k++) a.slot[k] = xp.slot[k];
+    a.seq = ++s->xseq;
+    a.spinNs = s->spin_ns;
+    const int threads = 256, blocks = (hp.n * s->H * 2 + threads - 1) / threads;
+    k_push_ghosts<<<blocks, threads, 0, cs>>>(a);
+    LAUNCHED("k_push_ghosts");
+    CK(cudaEventRecord(s->evPush, cs));
+    s->pending_seq = a.seq;
+    s->push_pending = true;
+    s->exch_pending = true;
+    return 0;
+  }
+  if (!s->comm) return fail("no ghost-exchange transport: call wsb_connect_peers (or pass an NCCL comm_id to wsb_create) before stepping a strip");
   {
     ProfScope prof(s, WSB_KERNEL_HALO, cs);
     const int n = s->H * kGhost * hp.n;
@@ -306,10 +461,25 @@ int exchange(wsb_sim* s, const HaloPlanes& hp) {
   s->exch_pending = true;
   return 0;
 }
+// the compute stream may touch the ghost columns again: the neighbours' data of the exchange in flight has arrived
 int join_exchange(wsb_sim* s) {
   if (s->exch_pending) {
-    CK(cudaStreamWaitEvent(s->stream, s->evExch, 0));
+    if (s->peer_mode) {
+      ProfScope prof(s, WSB_KERNEL_WAIT);
+      k_wait_ghosts<<<1, 1, 0, s->stream>>>(reinterpret_cast<unsigned*>(s->arena + s->plane_bytes * kArenaSlots), s->pending_seq, s->spin_ns);
+      LAUNCHED("k_wait_ghosts");
+    } else {
+      CK(cudaStreamWaitEvent(s->stream, s->evExch, 0));
+    }
     s->exch_pending = false;
+  }
+  return 0;
+}
+// the compute stream may overwrite this rank's edge columns again: its own push has read them
+int join_push(wsb_sim* s) {
+  if (s->push_pending) {
+    CK(cudaStreamWaitEvent(s->stream, s->evPush, 0));
+    s->push_pending = false;
   }
   return 0;
 }
@@ -402,12 +572,13 @@ int ref_iteration(wsb_sim* s) {
 }
 
 // --- fused schedule --------------------------------------------------------------------------
-dim3 tile_grid(const wsb_sim* s) { return dim3((s->pitch + kTX - 1) / kTX, (s->H + kTY - 1) / kTY); }
 
 int fused_iteration(wsb_sim* s) {
   set_iter_uniform(s);
   const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;
   const bool particles = s->dp.p.enablePrecipitation && s->ND > 0;
+  const int tilesY = (s->H + kTY - 1) / kTY;
+  constexpr int kNoGap = 0x7fffffff;
   // pressure(previous iteration) -> velocity -> curl -> vorticity -> boundary; also clears the
   // feedback / deposition cells it has consumed (app.js:5933-5934 folded in)
   {
@@ -421,28 +592,32 @@ int fused_iteration(wsb_sim* s) {
     maps.m[4] = s->wallMap3[1];
     maps.m[9] = s->light[0].map0[0];   // SUNLIGHT
     maps.m[10] = s->light[0].map0[1];  // NET_HEATING
-    auto launch_pvb = [&](int cx0, int cx1) {
-      c.g.cx0 = cx0;
-      c.g.cx1 = cx1;
-      k_fused_pvb<<<dim3((cx1 - cx0 + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, s->stream>>>(
+    // tile columns [cx0, cx1) minus [gapAt, gapAt + gapLen)
+    auto launch_pvb = [&](int cx0, int cx1, int gapAt, int gapLen) {
+      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+      k_fused_pvb<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, tilesY), kNT, kSmem1, s->stream>>>(
           c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
           s->base[0].p, s->water[0].p, s->wall[0]);
       return check_launch(s, "k_fused_pvb");
     };
     // While the previous iteration's ghost exchange is still in flight, run the tiles whose staged
-    // region (tile + 4 columns) stays clear of the ghost columns; then wait, then the two edges.
-    const int innerEnd = kTX + ((s->pitch - (kGhost + kHX) - kTX) / kTX) * kTX;
+    // region (tile + 4 columns) stays clear of the ghost columns; then wait for the neighbours'
+    // columns; then the two edge tile columns (one launch).
+    const int innerEnd = s->pvbInnerEnd;
     if (s->exch_pending && innerEnd > kTX) {
-      if (launch_pvb(kTX, innerEnd)) return 1;
+      if (launch_pvb(kTX, innerEnd, kNoGap, 0)) return 1;
       if (join_exchange(s)) return 1;
-      if (launch_pvb(0, kTX) || launch_pvb(innerEnd, s->pitch)) return 1;
+      if (launch_pvb(0, s->pitch, kTX, innerEnd - kTX)) return 1;
     } else {
       if (join_exchange(s)) return 1;
-      if (launch_pvb(0, s->pitch)) return 1;
+      if (launch_pvb(0, s->pitch, kNoGap, 0)) return 1;
     }
   }
   s->fb_dirty = false;
-  // advection (+ condensation ...) -> lighting
+  // advection (+ condensation ...) -> lighting.  On a strip with the peer transport the two edge tile
+  // columns (which produce the columns the neighbours need) go first, so that the push of the ghost
+  // columns runs beside the interior tiles.
+  const bool edgeFirst = s->peer_mode && s->advEdgeStart > kTX;
   {
     ProfScope prof(s, WSB_KERNEL_ADV);
     TileMaps<12> maps;
@@ -454,21 +629,33 @@ int fused_iteration(wsb_sim* s) {
     maps.m[9] = s->light[src].map2[0];   // SUNLIGHT
     maps.m[10] = s->light[src].map2[2];  // IR_DOWN
     maps.m[11] = s->light[src].map2[3];  // IR_UP
-    k_fused_adv<<<tile_grid(s), kNT, kSmem2, s->stream>>>(make_ctx(s, 0, 0, 0, src), s->dp, maps, s->use_tma ? 1 : 0, s->initial_T,
-                                                           s->sndT, s->sndW, s->sndV, s->base[1].p, s->water[1].p, s->wall[1],
-                                                           s->light[dst].p, s->maxv);
-    LAUNCHED("k_fused_adv");
+    GlobalCtx c = make_ctx(s, 0, 0, 0, src);
+    auto launch_adv = [&](int cx0, int cx1, int gapAt, int gapLen) {
+      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+      k_fused_adv<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, tilesY), kNT, kSmem2, s->stream>>>(
+          c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->sndT, s->sndW, s->sndV, s->base[1].p, s->water[1].p, s->wall[1],
+          s->light[dst].p, s->maxv);
+      return check_launch(s, "k_fused_adv");
+    };
+    if (join_push(s)) return 1;  // the previous push has finished reading the columns this kernel overwrites
+    if (edgeFirst) {
+      if (launch_adv(0, s->pitch, kTX, s->advEdgeStart - kTX)) return 1;
+      CK(cudaEventRecord(s->evEdge, s->stream));
+      if (launch_adv(kTX, s->advEdgeStart, kNoGap, 0)) return 1;
+    } else {
+      if (launch_adv(0, s->pitch, kNoGap, 0)) return 1;
+    }
   }
   s->even = !s->even;
   s->pressure_pending = true;
   if (particles && precipitation(s)) return 1;
   if (s->cfg.n_ranks > 1) {
-    HaloPlanes hp{};
-    add_planes(hp, s->base[1].p);
-    add_planes(hp, s->water[1].p);
-    hp.p[hp.n++] = s->wall[1];
-    add_planes(hp, s->light[dst].p);
-    if (exchange(s, hp)) return 1;
+    XPlanes xp;
+    add_planes(xp, s->base[1]);
+    add_planes(xp, s->water[1]);
+    add_wall(xp, s, 1);
+    add_planes(xp, s->light[dst]);
+    if (exchange(s, xp, edgeFirst)) return 1;
   }
   s->iter++;
   return 0;
@@ -496,9 +683,9 @@ int dry_iteration(wsb_sim* s) {
     std::swap(s->base[0], s->base[1]);
     s->pressure_pending = true;
     if (s->cfg.n_ranks > 1) {
-      HaloPlanes hp{};
-      add_planes(hp, s->base[1].p);
-      if (exchange(s, hp) || join_exchange(s)) return 1;
+      XPlanes xp;
+      add_planes(xp, s->base[1]);
+      if (exchange(s, xp, false) || join_exchange(s) || join_push(s)) return 1;
     }
   }
   s->iter++;
@@ -518,10 +705,13 @@ int make_map(wsb_sim* s, CUtensorMap* m, void* plane, bool isInt, int boxW, int 
   return 0;
 }
 
-int alloc_field(wsb_sim* s, wsb_sim::Field& f) {
+// slot >= 0: the four planes are slots slot .. slot+3 of the exchange arena (strips)
+int alloc_field(wsb_sim* s, wsb_sim::Field& f, int slot = -1) {
   const size_t n = cells(s);
+  f.slot = slot;
   for (int k = 0; k < 4; k++) {
-    CK(cudaMalloc(&f.p.c[k], n * sizeof(float)));
+    if (slot >= 0) f.p.c[k] = reinterpret_cast<float*>(s->arena + (size_t)(slot + k) * s->plane_bytes);
+    else CK(cudaMalloc(&f.p.c[k], n * sizeof(float)));
     if (s->use_tma && (make_map(s, &f.map2[k], f.p.c[k], false, kSW2, kSH2) || make_map(s, &f.map3[k], f.p.c[k], false, kSW1, kSH1) ||
                        make_map(s, &f.map0[k], f.p.c[k], false, kTX, kTY) || make_map(s, &f.mapD[k], f.p.c[k], false, kSWD, kSHD)))
       return 1;
@@ -543,9 +733,23 @@ int alloc_all(wsb_sim* s) {
     }
     s->use_tma = g_encode != nullptr;
   }
+  const bool strips = s->cfg.n_ranks > 1;
+  if (strips) {  // everything a ghost exchange can carry lives in one arena the neighbours map (cudaIpc), flags behind it
+    s->plane_bytes = (n * 4 + 255) / 256 * 256;
+    s->arena_bytes = s->plane_bytes * kArenaSlots + (size_t)kNumFlags * kFlagStride * 4;
+    CK(cudaMalloc(&s->arena, s->arena_bytes));
+    CK(cudaMemset(s->arena, 0, s->arena_bytes));
+  }
   for (int k = 0; k < 2; k++) {
-    if (alloc_field(s, s->base[k]) || alloc_field(s, s->water[k]) || alloc_field(s, s->light[k])) return 1;
-    CK(cudaMalloc(&s->wall[k], n * sizeof(int)));
+    if (alloc_field(s, s->base[k], strips ? 4 * k : -1) || alloc_field(s, s->water[k], strips && k == 1 ? 8 : -1) ||
+        alloc_field(s, s->light[k], strips ? 13 + 4 * k : -1))
+      return 1;
+    if (strips && k == 1) {
+      s->wall_slot[1] = 12;
+      s->wall[1] = reinterpret_cast<int*>(s->arena + (size_t)12 * s->plane_bytes);
+    } else {
+      CK(cudaMalloc(&s->wall[k], n * sizeof(int)));
+    }
     if (s->use_tma && (make_map(s, &s->wallMap2[k], s->wall[k], true, kSW2, kSH2) || make_map(s, &s->wallMap3[k], s->wall[k], true, kSW1, kSH1) ||
                        make_map(s, &s->wallMapD[k], s->wall[k], true, kSWD, kSHD)))
       return 1;
@@ -639,6 +843,34 @@ int upload_texels(wsb_sim* s, const Planes4& dst, const float* src, bool global_
   return 0;
 }
 
+constexpr unsigned kPeerMagic = 0x57534250u;  // "WSBP"
+struct PeerInfo {
+  unsigned magic;
+  int pid, device, rank, pitch, lw, H, reserved;
+  unsigned long long plane_bytes, arena_bytes, raw;
+  cudaIpcMemHandle_t handle;
+};
+
+// Strips stay bit-identical to the single-GPU run only while one iteration's dependency radius fits
+// the ghost zone: 3 (boundary kernel) + 1 + ceil(|v|) (back-trace footprint) <= kGhost, i.e. |v| <= 4
+// (strips.MAX_STRIP_VELOCITY).  Checked after every synchronisation of a strip, with the bounded-spin
+// error word of the peer transport.  The stream must be idle.
+constexpr float kMaxStripVelocity = 4.0f;
+int strip_checks(wsb_sim* s) {
+  if (s->cfg.n_ranks <= 1) return 0;
+  float v = 0.0f;
+  CK(cudaMemcpy(&v, s->maxv, 4, cudaMemcpyDeviceToHost));
+  if (!(v <= kMaxStripVelocity))
+    return fail("strip %d: max |v| = %g cells/iteration exceeds the ghost-zone budget of %g; owned cells no longer match the single-GPU run",
+                s->cfg.rank, v, kMaxStripVelocity);
+  if (s->arena) {
+    unsigned err = 0;
+    CK(cudaMemcpy(&err, reinterpret_cast<unsigned*>(s->arena + s->plane_bytes * kArenaSlots) + kFlagErr * kFlagStride, 4, cudaMemcpyDeviceToHost));
+    if (err) return fail("strip %d: a ghost-exchange wait ran out (a neighbour is missing or stepped a different number of iterations)", s->cfg.rank);
+  }
+  return 0;
+}
+
 int use_device(const wsb_sim* s) {
   CK(cudaSetDevice(s->cfg.device));
   return 0;
@@ -655,7 +887,7 @@ const char* wsb_build_info(void) {
 #define WSB_STR2(x) #x
 #define WSB_STR(x) WSB_STR2(x)
   return "libwsb200 abi 1 | sm_100a | nvcc " WSB_STR(__CUDACC_VER_MAJOR__) "." WSB_STR(__CUDACC_VER_MINOR__) "." WSB_STR(__CUDACC_VER_BUILD__)
-         " | fmad=false | tile 64x16 (dry sweep 64x28), 256 threads, TMA-staged channel planes | ghost 8";
+         " | fmad=false | tile 64x16 (dry sweep 64x28), 256 threads, TMA-staged channel planes | ghost 8 | strips: peer-memory push (NCCL send/recv optional)";
 }
 
 int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]) {
@@ -702,7 +934,12 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
 
   Geom& g = s->g;
   g.Wg = s->W; g.H = s->H; g.pitch = s->pitch; g.gx0 = s->x_begin - s->ghost; g.wrap = cfg->n_ranks == 1 ? 1 : 0;
-  g.cx0 = 0; g.cx1 = s->pitch;
+  g.cx0 = 0; g.cx1 = s->pitch; g.cxGapAt = 0x7fffffff; g.cxGapLen = 0;
+  g.ox0 = s->ghost; g.ox1 = s->ghost + s->lw;
+  // strips: tile columns [kTX, pvbInnerEnd) of the boundary kernel stage nothing from the ghost zones; tile columns
+  // 0 and [advEdgeStart, pitch) of the advection kernel produce the columns the neighbours receive
+  s->pvbInnerEnd = kTX + ((s->pitch - (kGhost + kHX) - kTX) / kTX) * kTX;
+  s->advEdgeStart = (s->lw / kTX) * kTX;
   g.texelX = (float)(1.0 / (double)s->W); g.texelY = (float)(1.0 / (double)s->H);   // app.js:5436 -> uniform2f
   g.Wf = (float)s->W; g.Hf = (float)s->H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;                                 // advectionShader.frag:69
@@ -727,6 +964,18 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
       rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e));
       break;
     }
+    {  // Load every steady-state kernel now.  With CUDA's lazy module loading the FIRST launch of a kernel can
+       // synchronise the context — behind a neighbour's spinning k_push_ghosts / k_wait_ghosts that would stall
+       // (several strips in one process: deadlock until the bounded wait runs out).
+      cudaFuncAttributes fa;
+      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_push_ghosts,
+                           (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation,
+                           (const void*)k_latch, (const void*)k_texels_to_planes, (const void*)k_planes_to_texels, (const void*)k_pressure_rect,
+                           (const void*)k_gather_points};
+      for (const void* f : fns)
+        if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) break;
+      if (e != cudaSuccess) { rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e)); break; }
+    }
     if ((rc = alloc_all(s))) break;
     if ((rc = zero_transients(s))) break;
     if (cfg->n_ranks > 1) {
@@ -734,15 +983,26 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
       cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
       if ((e = cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, prHi)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s->evExch, cudaEventDisableTiming)) != cudaSuccess) {
+          (e = cudaEventCreateWithFlags(&s->evExch, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evEdge, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evPush, cudaEventDisableTiming)) != cudaSuccess) {
         rc = fail("wsb_create: %s", cudaGetErrorString(e));
         break;
       }
-      if ((rc = load_nccl())) break;
-      Id128 id;
-      memcpy(id.internal, cfg->comm_id, WSB_COMM_ID_BYTES);
-      int r = g_nccl.CommInitRank(&s->comm, cfg->n_ranks, id, cfg->rank);
-      if (r != 0) { rc = fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); break; }
+      if (const char* lim = getenv("WSB_SPIN_LIMIT_MS")) {
+        const long ms = atol(lim);
+        if (ms > 0) s->spin_ns = (unsigned long long)ms * 1000000ull;
+      }
+      // an all-zero comm_id = no NCCL communicator: the ghost exchange then needs wsb_connect_peers
+      bool haveId = false;
+      for (int i = 0; i < WSB_COMM_ID_BYTES; i++) haveId |= cfg->comm_id[i] != 0;
+      if (haveId) {
+        if ((rc = load_nccl())) break;
+        Id128 id;
+        memcpy(id.internal, cfg->comm_id, WSB_COMM_ID_BYTES);
+        int r = g_nccl.CommInitRank(&s->comm, cfg->n_ranks, id, cfg->rank);
+        if (r != 0) { rc = fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); break; }
+      }
     }
     cudaError_t e2 = cudaStreamSynchronize(s->stream);
     if (e2 != cudaSuccess) { rc = fail("wsb_create: %s", cudaGetErrorString(e2)); break; }
@@ -761,10 +1021,17 @@ int wsb_destroy(wsb_sim* s) {
   if (s->evCompute) cudaEventDestroy(s->evCompute);
   if (s->evExch) cudaEventDestroy(s->evExch);
   if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+  auto in_arena = [&](const void* q) { return s->arena && (const unsigned char*)q >= s->arena && (const unsigned char*)q < s->arena + s->arena_bytes; };
+  auto free_plane = [&](void* q) { if (!in_arena(q)) cudaFree(q); };
   for (int k = 0; k < 2; k++) {
-    for (int ch = 0; ch < 4; ch++) { cudaFree(s->base[k].p.c[ch]); cudaFree(s->water[k].p.c[ch]); cudaFree(s->light[k].p.c[ch]); }
-    cudaFree(s->wall[k]); cudaFree(s->drops[k]);
+    for (int ch = 0; ch < 4; ch++) { free_plane(s->base[k].p.c[ch]); free_plane(s->water[k].p.c[ch]); free_plane(s->light[k].p.c[ch]); }
+    free_plane(s->wall[k]); cudaFree(s->drops[k]);
   }
+  if (s->peerL_ipc && s->peerL) cudaIpcCloseMemHandle(s->peerL);
+  if (s->peerR_ipc && s->peerR && s->peerR != s->peerL) cudaIpcCloseMemHandle(s->peerR);
+  cudaFree(s->arena);
+  if (s->evEdge) cudaEventDestroy(s->evEdge);
+  if (s->evPush) cudaEventDestroy(s->evPush);
   cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
   cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
   cudaFree(s->lightning); cudaFree(s->inactive); cudaFree(s->maxv); cudaFree(s->scratch);
@@ -800,7 +1067,7 @@ int finish_upload(wsb_sim* s, const float* drops) {
 int wsb_upload(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
   if (!s || !base || !water || !wall) return fail("wsb_upload: null argument");
   if (s->ND > 0 && !drops) return fail("wsb_upload: droplets required (n_droplets = %d)", s->ND);
-  if (use_device(s) || join_exchange(s)) return 1;
+  if (use_device(s) || join_exchange(s) || join_push(s)) return 1;
   if (upload_texels(s, s->base[0].p, base, true) || upload_texels(s, s->water[0].p, water, true) ||
       upload_field(s, s->wall[0], wall, 4))
     return 1;
@@ -810,7 +1077,7 @@ int wsb_upload(wsb_sim* s, const float* base, const float* water, const int8_t* 
 int wsb_upload_local(wsb_sim* s, const float* base, const float* water, const int8_t* wall, const float* drops) {
   if (!s || !base || !water || !wall) return fail("wsb_upload_local: null argument");
   if (s->ND > 0 && !drops) return fail("wsb_upload_local: droplets required (n_droplets = %d)", s->ND);
-  if (use_device(s) || join_exchange(s)) return 1;
+  if (use_device(s) || join_exchange(s) || join_push(s)) return 1;
   const size_t n = cells(s);
   if (upload_texels(s, s->base[0].p, base, false) || upload_texels(s, s->water[0].p, water, false)) return 1;
   CK(cudaMemcpyAsync(s->wall[0], wall, n * 4, cudaMemcpyHostToDevice, s->stream));
@@ -864,7 +1131,7 @@ int wsb_step(wsb_sim* s, int32_t n_iters) {
   for (int i = 0; i < n_iters; i++) {
     if (s->schedule == WSB_SCHEDULE_REFERENCE ? ref_iteration(s) : fused_iteration(s)) return 1;
   }
-  if (join_exchange(s)) return 1;  // everything enqueued so far is ordered on the compute stream again
+  if (join_exchange(s) || join_push(s)) return 1;  // everything enqueued so far is ordered on the compute stream again
   CK(cudaEventRecord(s->ev1, s->stream));
   s->timed = true;
   return 0;
@@ -888,6 +1155,66 @@ int wsb_sync(wsb_sim* s) {
   if (!s) return fail("wsb_sync: null sim");
   if (use_device(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
+  return strip_checks(s);
+}
+
+int wsb_peer_info(wsb_sim* s, uint8_t out[WSB_PEER_INFO_BYTES]) {
+  if (!s || !out) return fail("wsb_peer_info: null argument");
+  if (s->cfg.n_ranks <= 1 || !s->arena) return fail("wsb_peer_info: not a strip of a multi-GPU run");
+  if (use_device(s)) return 1;
+  PeerInfo pi{};
+  pi.magic = kPeerMagic;
+  pi.pid = (int)getpid();
+  pi.device = s->cfg.device;
+  pi.rank = s->cfg.rank;
+  pi.pitch = s->pitch; pi.lw = s->lw; pi.H = s->H;
+  pi.plane_bytes = s->plane_bytes; pi.arena_bytes = s->arena_bytes;
+  pi.raw = (unsigned long long)(uintptr_t)s->arena;
+  CK(cudaIpcGetMemHandle(&pi.handle, s->arena));
+  static_assert(sizeof(PeerInfo) <= WSB_PEER_INFO_BYTES, "PeerInfo must fit the ABI blob");
+  memset(out, 0, WSB_PEER_INFO_BYTES);
+  memcpy(out, &pi, sizeof(pi));
+  return 0;
+}
+
+int wsb_connect_peers(wsb_sim* s, const uint8_t* left, const uint8_t* right) {
+  if (!s || !left || !right) return fail("wsb_connect_peers: null argument");
+  if (s->cfg.n_ranks <= 1 || !s->arena) return fail("wsb_connect_peers: not a strip of a multi-GPU run");
+  if (s->peer_mode) return fail("wsb_connect_peers: already connected");
+  if (use_device(s)) return 1;
+  PeerInfo L, R;
+  memcpy(&L, left, sizeof(L));
+  memcpy(&R, right, sizeof(R));
+  const int wantL = (s->cfg.rank + s->cfg.n_ranks - 1) % s->cfg.n_ranks, wantR = (s->cfg.rank + 1) % s->cfg.n_ranks;
+  if (L.magic != kPeerMagic || R.magic != kPeerMagic) return fail("wsb_connect_peers: not a wsb_peer_info blob");
+  if (L.rank != wantL || R.rank != wantR) return fail("wsb_connect_peers: got ranks (%d, %d), neighbours of rank %d are (%d, %d)", L.rank, R.rank, s->cfg.rank, wantL, wantR);
+  if (L.H != s->H || R.H != s->H) return fail("wsb_connect_peers: neighbour grids have a different height");
+  auto open = [&](const PeerInfo& pi, unsigned char** ptr, bool* ipc) -> int {
+    if (pi.pid == (int)getpid()) {  // same process (several sims in one host process): plain pointers
+      if (pi.device != s->cfg.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, s->cfg.device, pi.device));
+        if (!can) return fail("wsb_connect_peers: device %d cannot access device %d", s->cfg.device, pi.device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      *ptr = (unsigned char*)(uintptr_t)pi.raw;
+      *ipc = false;
+    } else {
+      void* q = nullptr;
+      CK(cudaIpcOpenMemHandle(&q, pi.handle, cudaIpcMemLazyEnablePeerAccess));
+      *ptr = (unsigned char*)q;
+      *ipc = true;
+    }
+    return 0;
+  };
+  if (open(L, &s->peerL, &s->peerL_ipc)) return 1;
+  if (R.rank == L.rank) { s->peerR = s->peerL; s->peerR_ipc = false; }  // two ranks: both neighbours are the same peer
+  else if (open(R, &s->peerR, &s->peerR_ipc)) return 1;
+  s->pbL = L.plane_bytes; s->pbR = R.plane_bytes;
+  s->pitchL = L.pitch; s->pitchR = R.pitch; s->lwL = L.lw;
+  s->peer_mode = true;
   return 0;
 }
 
@@ -972,7 +1299,7 @@ int wsb_read_rect(wsb_sim* s, int32_t field, int32_t view, int32_t x, int32_t y,
     CK(cudaMemcpy2DAsync(d, (size_t)w * elt, sp, (size_t)s->pitch * elt, (size_t)cw * elt, h, cudaMemcpyDeviceToHost, s->stream));
   }
   CK(cudaStreamSynchronize(s->stream));
-  return 0;
+  return strip_checks(s);
 }
 
 int wsb_read_points(wsb_sim* s, int32_t field, int32_t view, int32_t n, const int32_t* xy, float* dst) {
@@ -1080,7 +1407,7 @@ int wsb_set_profiling(wsb_sim* s, int32_t on) {
 
 int wsb_kernel_time_ms(wsb_sim* s, int32_t kernel, float* total_ms, int32_t* launches) {
   if (!s || !total_ms || !launches) return fail("wsb_kernel_time_ms: null argument");
-  if (kernel < 0 || kernel > WSB_KERNEL_HALO) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
+  if (kernel < 0 || kernel > WSB_KERNEL_WAIT) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
   if (use_device(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
   double sum = 0.0;
@@ -1103,7 +1430,7 @@ int wsb_last_step_ms(wsb_sim* s, float* out) {
   if (use_device(s)) return 1;
   CK(cudaEventSynchronize(s->ev1));
   CK(cudaEventElapsedTime(out, s->ev0, s->ev1));
-  return 0;
+  return strip_checks(s);
 }
 
 }  // extern "C"

@@ -16,7 +16,9 @@ struct Geom {
   int pitch;      // columns of the local arrays (owned + 2*ghost)
   int gx0;        // global x of local column 0 (negative in the left ghost zone of rank 0)
   int wrap;       // 1: single domain, local x indices wrap modulo pitch (== Wg)
-  int cx0, cx1;   // local columns this launch computes
+  int cx0, cx1;   // local columns this launch computes ...
+  int cxGapAt, cxGapLen;  // ... minus [cxGapAt, cxGapAt + cxGapLen): one launch covers the two edge tile columns of a strip
+  int ox0, ox1;   // owned columns (without the ghost zones): max |v| is only taken over these
   float texelX, texelY;    // uniform texelSize: (float)(1.0/W), (float)(1.0/H)   app.js:5436
   float ltexelX, ltexelY;  // advectionShader.frag:69  vec2(1.)/resolution in fp32
   float Hf, Wf;
@@ -43,6 +45,12 @@ __device__ __forceinline__ int wrap_x(const Geom& g, int x) {
 __device__ __forceinline__ int gather_x(const Geom& g, int x) {
   if (g.wrap) return mod_i(x, g.pitch);
   return min(max(x, 0), g.pitch - 1);
+}
+// first local column of the tile column blockIdx.x of this launch
+__device__ __forceinline__ int tile_col0(const Geom& g, int bx, int tileW) {
+  int c0 = g.cx0 + bx * tileW;
+  if (c0 >= g.cxGapAt) c0 += g.cxGapLen;
+  return c0;
 }
 __device__ __forceinline__ int global_x(const Geom& g, int lx) {
   int gx = g.gx0 + lx;

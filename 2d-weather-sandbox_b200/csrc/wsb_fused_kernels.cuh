@@ -404,48 +404,6 @@ constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;
 #define WSB_DRY_CTAS 4   // resident CTAs per SM the register allocation is bounded for
 #endif
 
-#ifndef WSB_DRY_PAIRADV
-#define WSB_DRY_PAIRADV 0   // experimental (emulator-verified, not yet timed): two horizontally adjacent cells per thread in the advection phase
-#endif
-#if WSB_DRY_PAIRADV
-// One cell of the dry advection from values its thread already holds: the cell's own post-velocity
-// velocity and the six staggered neighbours of advectionShader.frag:76-89.  Same arithmetic as the
-// single-cell loop of k_fused_dry.
-struct DryCellIn { float vx00, vy00, vxXm, vyYm, vyXp, vxYp, vxXmYp, vyXpYm; int w0; };
-template <int SW, int PS>
-__device__ __forceinline__ float4 dry_cell(const GlobalCtx& glob, const DevParams& d, int applyPressure, const float* sVX, const float* sT2,
-                                           const int* sWl, bool walls, int c, int x, int y, float gxf, float gyf, const DryCellIn& in,
-                                           float& vm) {
-  const float* pc = sVX + c;
-  if (wl_is_wall(in.w0))  // wall: pass-through of the post-velocity cell (advectionShader.frag:189-197)
-    return make_float4(in.vx00, in.vy00, pc[2 * PS], ((in.w0 & 0xff) == WALLTYPE_LAND) ? 1000.0f : sT2[c]);
-  vm = fmaxf(vm, fmaxf(fabsf(in.vx00), fabsf(in.vy00)));
-  const AdvVel a = adv_velocities(in.vx00, in.vy00, in.vxXm, in.vyYm, in.vyXp, in.vxYp, in.vxXmYp, in.vyXpYm);
-  if (adv_vmax(a) < glob.g.nearV) {
-    const float fragCoordX = gxf + 0.5f, fragCoordY = gyf + 0.5f, gxm1 = gxf - 1.0f, gym1 = gyf - 1.0f;
-    const NearTap n1 = near_tap(fragCoordX - a.Vxx, fragCoordY - a.Vxy, gxf, gxm1, gyf, gym1);
-    const NearTap n2 = near_tap(fragCoordX - a.Vyx, fragCoordY - a.Vyy, gxf, gxm1, gyf, gym1);
-    const NearTap n3 = near_tap(fragCoordX - a.Px, fragCoordY - a.Py, gxf, gxm1, gyf, gym1);
-    const float* q1 = near_ptr(n1, pc, pc - SW);
-    const float* q2 = near_ptr(n2, pc, pc - SW) + PS;
-    const float* q3 = near_ptr(n3, pc, pc - SW);
-    float4 base;
-    base.x = mix2d(q1[0], q1[1], q1[SW], q1[SW + 1], n1.fx, n1.fx, n1.fy);
-    base.y = mix2d(q2[0], q2[1], q2[SW], q2[SW + 1], n2.fx, n2.fx, n2.fy);
-    const WallMix m = walls ? tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 4 * PS), 0, n3.fx, n3.fy) : WallMix{n3.fx, n3.fx, n3.fy};
-    const float* qP = q3 + 2 * PS;
-    const float* qT = q3 + 5 * PS;
-    base.z = mix2d(qP[0], qP[1], qP[SW], qP[SW + 1], m.ab, m.cd, m.abcd);
-    base.w = mix2d(qT[0], qT[1], qT[SW], qT[SW + 1], m.ab, m.cd, m.abcd);
-    return base;
-  }
-  float vmSlow = 0.0f;
-  const float4 base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
-  vm = fmaxf(vm, vmSlow);
-  return base;
-}
-#endif
-
 // glob: base = base_1 (advection output, pressure pending), wall = wall_1.
 // maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
 // (Tried and dropped, profiles/r2_dry_variants.md: results leaving through shared-memory tiles and
@@ -471,7 +429,7 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTYD - kHD;
+  const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTYD - kHD;
 
   if (tid == 0) { *sMax = 0u; *sAnyWall = 0u; }
   if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
@@ -511,47 +469,6 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
   const bool walls = true;
 #endif
   float vm = 0.0f;
-#if WSB_DRY_PAIRADV
-  {  // thread (txp, ty0) advects the cell pair (2 txp, 2 txp + 1) of rows ty0, ty0 + 8, ...: the fixed stencil of the two
-     // cells is loaded with 8-byte accesses and shared, the results leave as 8-byte stores
-    constexpr int kPairs = kTX / 2, kRowStep2 = kNT / kPairs;
-    const int txp = tid % kPairs, ty0 = tid / kPairs;
-    const int x = X0 + kHX + 2 * txp;
-    const bool vec = ((g.pitch | g.cx0) & 1) == 0 && x + 1 < g.cx1;  // even row pitch and first column: 8-byte aligned pairs
-    if (x < g.cx1) {
-      const float gxfA = (float)global_x(g, x), gxfB = (float)global_x(g, x + 1);
-#pragma unroll 1
-      for (int ty = ty0; ty < kTYD; ty += kRowStep2) {
-        const int y = Y0 + kHD + ty;
-        if (y >= g.H) break;
-        const int c = (ty + kHD) * SW + kHX + 2 * txp;  // even: the pair is 8-byte aligned in every plane
-        const float gyf = (float)y;
-        int2 w = make_int2(0x0100, 0x0100);  // air texels (DISTANCE 1)
-        if (walls) w = ld2(sWl + c);
-        const float2 vx = ld2(sVX + c), vy = ld2(sVY + c), vyb = ld2(sVY + c - SW), vxu = ld2(sVX + c + SW);
-        const float vxm = sVX[c - 1], vyr = sVY[c + 2], vybr = sVY[c - SW + 2], vxum = sVX[c + SW - 1];
-        const float4 a = dry_cell<SW, kPSD>(glob, d, applyPressure, sVX, sT2, sWl, walls, c, x, y, gxfA, gyf,
-                                            DryCellIn{vx.x, vy.x, vxm, vyb.x, vy.y, vxu.x, vxum, vyb.y, w.x}, vm);
-        const size_t ci = (size_t)y * g.pitch + x;
-        if (x + 1 < g.cx1) {
-          const float4 b = dry_cell<SW, kPSD>(glob, d, applyPressure, sVX, sT2, sWl, walls, c + 1, x + 1, y, gxfB, gyf,
-                                              DryCellIn{vx.y, vy.y, vx.x, vyb.y, vyr, vxu.y, vxu.x, vybr, w.y}, vm);
-          if (vec) {
-            *reinterpret_cast<float2*>(baseOut.c[0] + ci) = make_float2(a.x, b.x);
-            *reinterpret_cast<float2*>(baseOut.c[1] + ci) = make_float2(a.y, b.y);
-            *reinterpret_cast<float2*>(baseOut.c[2] + ci) = make_float2(a.z, b.z);
-            *reinterpret_cast<float2*>(baseOut.c[3] + ci) = make_float2(a.w, b.w);
-          } else {
-            baseOut.st(ci, a);
-            baseOut.st(ci + 1, b);
-          }
-        } else {
-          baseOut.st(ci, a);
-        }
-      }
-    }
-  }
-#else
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
   if (x < g.cx1) {
@@ -625,7 +542,7 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
       baseOut.st((size_t)y * g.pitch + x, base);
     }
   }
-#endif  // WSB_DRY_PAIRADV
+  if (x < g.ox0 || x >= g.ox1) vm = 0.0f;  // ghost columns hold the neighbour's cells (and edge garbage)
   report_vmax_cta(vm, maxv, sMax);
 }
 
@@ -709,7 +626,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH1;
+  const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTY - kH1;
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
   const bool colOk = x < g.cx1;
@@ -870,7 +787,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
 
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = g.cx0 + blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTY - kH2;
+  const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTY - kH2;
 
   // (interior rows never touch the CLAMP_TO_EDGE rule of the light texture, so one box shape serves all planes)
   unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
@@ -1040,6 +957,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
       lightOut.st(ci, lighting_cell(lc, g, d, x, y, fragCoordX, base.w, water, wl, TBelow));
     }
   }
+  if (x < g.ox0 || x >= g.ox1) vm = 0.0f;  // ghost columns hold the neighbour's cells (and edge garbage)
   report_vmax_cta(vm, maxv, sMax);
 }
 

@@ -1,6 +1,8 @@
-"""Multi-GPU host plumbing: one process per GPU (torchrun), torch.distributed only carries the
-NCCL bootstrap id and the readback gathers; the per-iteration halo exchange itself runs inside
-libwsb200.so (ncclSend / ncclRecv on the simulation stream, csrc/wsb200.cu: exchange()).
+"""Multi-GPU host plumbing: one process per GPU (torchrun).  torch.distributed only carries the
+bootstrap blobs (peer-memory windows, or the NCCL id) and the readback gathers; the per-iteration
+ghost exchange itself runs inside libwsb200.so (csrc/wsb200.cu: exchange()): by default one kernel
+that stores the edge columns straight into the neighbours' ghost columns over NVLink
+(transport "peer"), optionally ncclSend / ncclRecv through staging buffers (transport "nccl").
 
 The reference is single-GPU; this is the x-strip decomposition of SURVEY 8e.
 """
@@ -26,9 +28,23 @@ def broadcast_comm_id(create_fn, group=None) -> bytes:
     return bytes(cid)
 
 
-def create_distributed(width: int, height: int, *, device: int, gui_controls=None, group=None, **kw):
+def connect_ring(sim, group=None) -> None:
+    """All-gather every rank's peer window and link `sim` with its two ring neighbours."""
+    import torch.distributed as dist
+
+    n, r = dist.get_world_size(group), dist.get_rank(group)
+    infos = [None] * n
+    dist.all_gather_object(infos, sim.peer_info(), group=group)
+    left, right = strips.neighbours(r, n)
+    sim.connect_peers(infos[left], infos[right])
+
+
+def create_distributed(width: int, height: int, *, device: int, gui_controls=None, group=None, transport: str | None = None, **kw):
     """A Simulation for this rank's strip of a width x height grid (torch.distributed must be
-    initialised; with world size 1 this is a plain single-GPU simulation)."""
+    initialised; with world size 1 this is a plain single-GPU simulation).  transport: "peer"
+    (default; WSB_EXCHANGE overrides) or "nccl"."""
+    import os
+
     import torch.distributed as dist
 
     from .sim import Simulation, comm_id_create
@@ -37,9 +53,16 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
     r = dist.get_rank(group) if dist.is_initialized() else 0
     if n == 1:
         return Simulation(width, height, kw.pop("n_droplets", 0), device=device, gui_controls=gui_controls, **kw)
-    cid = broadcast_comm_id(comm_id_create, group)
+    transport = transport or os.environ.get("WSB_EXCHANGE", "peer")
+    if transport not in ("peer", "nccl"):
+        raise ValueError(f"unknown ghost-exchange transport {transport!r}")
     kw.pop("n_droplets", None)
-    return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+    if transport == "nccl":
+        cid = broadcast_comm_id(comm_id_create, group)
+        return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+    sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=None, gui_controls=gui_controls, **kw)
+    connect_ring(sim, group)
+    return sim
 
 
 def gather_strips(local: np.ndarray, width: int, group=None):

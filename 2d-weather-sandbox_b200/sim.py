@@ -36,8 +36,9 @@ VIEW_FRAMEBUFF_0, VIEW_FRAMEBUFF_1, VIEW_LATEST = range(3)
 SCHEDULE_FUSED, SCHEDULE_REFERENCE = 0, 1
 (PASS_VELOCITY, PASS_CURL, PASS_VORTICITY, PASS_BOUNDARY, PASS_ADVECTION, PASS_PRESSURE, PASS_LIGHTING,
  PASS_PRECIPITATION, PASS_ITER_INC, PASS_ADVECTION_DRY) = range(10)
-KERNEL_PVB, KERNEL_ADV, KERNEL_DRY, KERNEL_PRECIP, KERNEL_HALO = range(5)
+KERNEL_PVB, KERNEL_ADV, KERNEL_DRY, KERNEL_PRECIP, KERNEL_HALO, KERNEL_WAIT = range(6)
 COMM_ID_BYTES = 128
+PEER_INFO_BYTES = 256
 ABI_VERSION = 1
 
 _FIELD_SPEC = {  # channels, dtype
@@ -67,7 +68,7 @@ def library_path() -> str:
 
 # every symbol include/wsb200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "wsb_comm_id_create", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
+    "wsb_comm_id_create", "wsb_peer_info", "wsb_connect_peers", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
     "wsb_set_profiling", "wsb_kernel_time_ms", "wsb_set_params",
     "wsb_set_profiles", "wsb_set_frame_inputs", "wsb_step", "wsb_sync", "wsb_debug_run_pass",
     "wsb_step_dry", "wsb_read_rect", "wsb_read_points", "wsb_read_droplets", "wsb_get_inactive_droplets",
@@ -91,6 +92,8 @@ def load_library():
     vp, i32, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_float)
     L.wsb_comm_id_create.argtypes = [ctypes.POINTER(ctypes.c_uint8)]
     L.wsb_create.argtypes = [ctypes.POINTER(WsbConfig), ctypes.POINTER(vp)]
+    L.wsb_peer_info.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8)]
+    L.wsb_connect_peers.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
     L.wsb_destroy.argtypes = [vp]
     L.wsb_upload.argtypes = [vp, vp, vp, vp, vp]
     L.wsb_upload_local.argtypes = [vp, vp, vp, vp, vp]
@@ -147,15 +150,16 @@ class Simulation:
         cfg.abi_version = ABI_VERSION
         cfg.width, cfg.height, cfg.n_droplets = self.W, self.H, self.ND
         cfg.device, cfg.rank, cfg.n_ranks, cfg.schedule = device, rank, n_ranks, schedule
-        if n_ranks > 1:
-            if comm_id is None or len(comm_id) != COMM_ID_BYTES:
-                raise WsbError("multi-GPU simulation needs the comm_id created on rank 0")
+        if n_ranks > 1 and comm_id is not None:  # None: no NCCL communicator, the strip is linked with connect_peers()
+            if len(comm_id) != COMM_ID_BYTES:
+                raise WsbError("comm_id must be the 128 bytes created on rank 0")
             ctypes.memmove(cfg.comm_id, comm_id, COMM_ID_BYTES)
         self.h = ctypes.c_void_p()
         self._check(self.L.wsb_create(ctypes.byref(cfg), ctypes.byref(self.h)))
         self.x_begin, self.local_width = strips.strip_bounds(self.W, n_ranks, rank)
         self.gui = dict(gui_controls) if gui_controls is not None else P.resolve_settings(None)
         self.sun_clock = None
+        self._soundings = (None, None, None)  # realWorldSounding_{T,W,Vel}v as last set (set_profiles)
         self.set_gui_uniforms(self.gui)
         self.update_sunlight()
 
@@ -197,6 +201,19 @@ class Simulation:
             self.close()
         except Exception:
             pass
+
+    # -- multi-GPU ghost exchange over peer memory ---------------------------------------------
+    def peer_info(self) -> bytes:
+        """This strip's exchange window (IPC handle + layout) for its two ring neighbours."""
+        buf = (ctypes.c_uint8 * PEER_INFO_BYTES)()
+        self._check(self.L.wsb_peer_info(self.h, buf))
+        return bytes(buf)
+
+    def connect_peers(self, left_info: bytes, right_info: bytes):
+        """Map the neighbours' windows: from now on ghost columns travel as direct peer stores."""
+        if len(left_info) != PEER_INFO_BYTES or len(right_info) != PEER_INFO_BYTES:
+            raise WsbError("connect_peers: blobs must come from peer_info()")
+        self._check(self.L.wsb_connect_peers(self.h, left_info, right_info))
 
     # -- state ---------------------------------------------------------------------------------
     def upload(self, base, water, wall, drops=None):
@@ -258,8 +275,9 @@ class Simulation:
         p = P.derive_params(self.gui)
         self.params = p
         self._check(self.L.wsb_set_params(self.h, ctypes.byref(p)))
+        # setGuiUniforms does not touch the realWorldSounding_* uniforms: pass the last sounding again
         t0 = P.initial_T_profile(self.H, self.gui)
-        self._check(self.L.wsb_set_profiles(self.h, _ptr(t0), None, None, None))
+        self._check(self.L.wsb_set_profiles(self.h, _ptr(t0), *[_ptr(a) for a in self._soundings]))
 
     def set_params(self, p: P.WsbParams):
         self.params = p
@@ -270,6 +288,7 @@ class Simulation:
         for a in arrs:
             if a is not None and a.shape != (self.H + 1,):
                 raise WsbError("profiles must have height+1 entries")
+        self._soundings = tuple(arrs[1:])
         self._check(self.L.wsb_set_profiles(self.h, *[_ptr(a) for a in arrs]))
 
     def update_sunlight(self, delta_hours: float | None = None):
@@ -281,7 +300,12 @@ class Simulation:
                 self.sun_clock = P.SunClock(self.gui)
             if delta_hours:
                 self.sun_clock.advance(delta_hours)
-        self.frame_inputs = P.frame_inputs(self.gui)
+        fresh = P.frame_inputs(self.gui)
+        cur = getattr(self, "frame_inputs", None)
+        if cur is None:
+            self.frame_inputs = fresh
+        else:  # updateSunlight only sets sunAngle / sunIntensity (app.js:6557-6561): brush and airplane inputs stay
+            cur.sunAngle, cur.sunIntensity = fresh.sunAngle, fresh.sunIntensity
         self._check(self.L.wsb_set_frame_inputs(self.h, ctypes.byref(self.frame_inputs)))
 
     def set_frame_inputs(self, fi: P.WsbFrameInputs):

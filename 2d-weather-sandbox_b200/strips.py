@@ -6,15 +6,19 @@ a ring: the left neighbour of rank 0 is rank N-1.  Every strip keeps the full he
 periodic y-wrap stays local.
 
 Each rank stores its strip with GHOST columns on both sides.  One iteration of the fused
-schedule has a dependency radius of at most 3 (pressure+velocity+curl+vorticity+boundary kernel)
-+ 1 + floor(|v|max) (advection back-trace) + 2 (sun-ray bilinear fetch of the lighting pass),
-so with GHOST = 8 a single exchange of GHOST columns per iteration keeps every owned cell
-bit-identical to the single-GPU run while |v| < 3 cells/iteration (the shipped saves peak at
-0.36).  libwsb200 uses exactly these numbers (csrc/wsb200.cu: kGhost).
+schedule has a dependency radius of 3 (pressure+velocity+curl+vorticity+boundary kernel: its
+output is valid from the 4th ghost column inwards) + 1 + ceil(|v|max) (the bilinear footprint of
+the advection back-trace; the sun-ray fetch of the lighting pass needs 2), so with GHOST = 8 a
+single exchange of GHOST columns per iteration keeps every owned cell bit-identical to the
+single-GPU run while |v| <= MAX_STRIP_VELOCITY = 4 cells/iteration (the shipped saves peak at
+0.36).  libwsb200 uses exactly these numbers (csrc/wsb200.cu: kGhost, kMaxStripVelocity) and
+every synchronising call of a strip fails once the running maximum of |v| over its own columns
+exceeds the budget.
 """
 from __future__ import annotations
 
 GHOST = 8
+MAX_STRIP_VELOCITY = 4.0
 
 
 def strip_bounds(width: int, n_ranks: int, rank: int) -> tuple[int, int]:

@@ -49,7 +49,8 @@ typedef struct wsb_config {
   int32_t rank;          /* 0 .. n_ranks-1 */
   int32_t n_ranks;       /* 1 = single GPU */
   int32_t schedule;      /* WSB_SCHEDULE_* */
-  uint8_t comm_id[WSB_COMM_ID_BYTES]; /* from wsb_comm_id_create on rank 0 (n_ranks > 1) */
+  uint8_t comm_id[WSB_COMM_ID_BYTES]; /* from wsb_comm_id_create on rank 0 (n_ranks > 1); all zero = no NCCL
+                                         communicator (the strip must then be linked with wsb_connect_peers) */
 } wsb_config;
 
 enum {
@@ -135,6 +136,19 @@ enum {
 /* Rank 0 of a multi-GPU job creates the bootstrap id and hands it to the other processes by any
  * host-side channel (the Python host uses torch.distributed broadcast). */
 int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]);
+
+/* Ghost-exchange transport of a multi-GPU run over peer memory (NVLink): every rank publishes a
+ * window onto the planes its neighbours write ghost columns into (wsb_peer_info), the host
+ * plumbing carries the blobs to the ring neighbours (torch.distributed all_gather in the Python
+ * host), and wsb_connect_peers maps them (cudaIpcOpenMemHandle between processes, plain pointers
+ * inside one process).  From then on every iteration's advection kernel is followed by ONE kernel
+ * that stores this rank's outermost owned columns straight into the neighbours' ghost columns
+ * and raises a sequence flag there; the next boundary kernel's edge tiles wait for the flag.
+ * Without wsb_connect_peers a strip uses ncclSend/ncclRecv (needs a comm_id).  The reference is
+ * single-GPU: no reference interaction is replaced. */
+#define WSB_PEER_INFO_BYTES 256
+int wsb_peer_info(wsb_sim* sim, uint8_t out[WSB_PEER_INFO_BYTES]);
+int wsb_connect_peers(wsb_sim* sim, const uint8_t* left_info, const uint8_t* right_info);
 
 /* app.js:5149-5317 + 4885-5002: allocate state; light, feedback, deposition, lightning, curl and
  * vortForce start zero-filled (texImage2D(..., null)); iterNum = 0, even = true. */
@@ -232,8 +246,11 @@ int wsb_set_iter(wsb_sim* sim, int64_t iter);
 /* Local strip of this rank: [x_begin, x_begin + local_width). */
 int wsb_get_strip(wsb_sim* sim, int32_t* x_begin, int32_t* local_width);
 
-/* Largest |v| component seen by the advection kernel since upload (cells / iteration); the fused
- * kernels stay exact for any value, multi-GPU strips require it below the ghost-zone budget. */
+/* Largest |v| component the advection kernel has seen in this rank's OWN columns since upload
+ * (cells / iteration).  The fused kernels stay exact for any value; multi-GPU strips are
+ * bit-identical to the single-GPU run while it is <= 4 (ghost 8 = 3 + 1 + ceil|v|): every
+ * synchronising call of a strip (wsb_sync, wsb_read_rect, wsb_last_step_ms) FAILS once it is
+ * exceeded, instead of returning silently diverged fields. */
 int wsb_get_max_velocity(wsb_sim* sim, float* out);
 
 /* Number of kernels launched by this sim since creation (bench evidence). */
@@ -253,7 +270,9 @@ enum {
   WSB_KERNEL_ADV = 1,    /* k_fused_adv: advection -> lighting */
   WSB_KERNEL_DRY = 2,    /* k_fused_dry: velocity -> advection(base) -> pressure */
   WSB_KERNEL_PRECIP = 3, /* k_precipitation + k_latch */
-  WSB_KERNEL_HALO = 4    /* pack + ncclSend/Recv + unpack */
+  WSB_KERNEL_HALO = 4,   /* ghost exchange on the communication stream: k_push_ghosts (peer transport) or
+                            pack + ncclSend/Recv + unpack (NCCL transport) */
+  WSB_KERNEL_WAIT = 5    /* k_wait_ghosts: time the compute stream waited for the neighbours' columns */
 };
 int wsb_set_profiling(wsb_sim* sim, int32_t on);
 int wsb_kernel_time_ms(wsb_sim* sim, int32_t kernel, float* total_ms, int32_t* launches);

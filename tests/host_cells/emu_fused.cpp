@@ -79,10 +79,9 @@ void fused_iteration(Sim& s) {
     maps.m[10] = map_of(s, s.light[0].p.c[1], kTX, kTY);
     const DevParams d = s.dp;
     const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = s.fb_dirty ? 1 : 0;
-    auto launch_pvb = [&](int cx0, int cx1) {
-      c.g.cx0 = cx0;
-      c.g.cx1 = cx1;
-      emu::launch(dim3((cx1 - cx0 + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem1, [&] {
+    auto launch_pvb = [&](int cx0, int cx1, int gapAt, int gapLen) {
+      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+      emu::launch(dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem1, [&] {
         k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
                     s.wall[0].data());
       });
@@ -92,12 +91,12 @@ void fused_iteration(Sim& s) {
     // exchange has landed (csrc/wsb200.cu); the exchange itself is done by the test between iterations
     const int kGhostCols = 8;
     const int innerEnd = kTX + ((s.W - (kGhostCols + kHX) - kTX) / kTX) * kTX;
+    constexpr int kNoGap = 0x7fffffff;
     if (!s.g.wrap && s.pressure_pending && innerEnd > kTX) {
-      launch_pvb(kTX, innerEnd);
-      launch_pvb(0, kTX);
-      launch_pvb(innerEnd, s.W);
+      launch_pvb(kTX, innerEnd, kNoGap, 0);
+      launch_pvb(0, s.W, kTX, innerEnd - kTX);  // both edge tile columns in one launch
     } else {
-      launch_pvb(0, s.W);
+      launch_pvb(0, s.W, kNoGap, 0);
     }
     s.fb_dirty = false;  // the kernel has consumed the feedback and zeroed the texels that were hit (app.js:5933-5934 folded in)
   }
@@ -114,11 +113,22 @@ void fused_iteration(Sim& s) {
     maps.m[11] = map_of(s, s.light[src].p.c[3], kSW2, kSH2);
     const DevParams d = s.dp;
     const int useTma = s.use_tma;
-    emu::launch(tile_grid(s, kTY), kNT, kSmem2, [&] {
-      k_fused_adv(c, d, maps, useTma, s.initial_T.data(), s.sndT.data(), s.sndW.data(), s.sndV.data(), s.base[1].p, s.water[1].p,
-                  s.wall[1].data(), s.light[dst].p, &s.maxv);
-    });
-    s.launches++;
+    auto launch_adv = [&](int cx0, int cx1, int gapAt, int gapLen) {
+      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+      emu::launch(dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem2, [&] {
+        k_fused_adv(c, d, maps, useTma, s.initial_T.data(), s.sndT.data(), s.sndW.data(), s.sndV.data(), s.base[1].p, s.water[1].p,
+                    s.wall[1].data(), s.light[dst].p, &s.maxv);
+      });
+      s.launches++;
+    };
+    // a strip with the peer transport: the edge tile columns (which produce the neighbours' ghost columns) first
+    const int advEdgeStart = ((s.W - 2 * 8) / kTX) * kTX;
+    if (!s.g.wrap && advEdgeStart > kTX) {
+      launch_adv(0, s.W, kTX, advEdgeStart - kTX);
+      launch_adv(kTX, advEdgeStart, 0x7fffffff, 0);
+    } else {
+      launch_adv(0, s.W, 0x7fffffff, 0);
+    }
   }
   s.even = !s.even;
   s.pressure_pending = true;
@@ -167,6 +177,7 @@ void* ef_create_strip(int Wg, int H, int x_begin, int lw, int ghost) {
   s->initial_T.assign(H + 2, 0.0f); s->sndT.assign(H + 2, 0.0f); s->sndW.assign(H + 2, 0.0f); s->sndV.assign(H + 2, 0.0f);
   Geom& g = s->g;  // as wsb_create
   g.Wg = Wg; g.H = H; g.pitch = W; g.gx0 = x_begin - ghost; g.wrap = ghost == 0 ? 1 : 0; g.cx0 = 0; g.cx1 = W;
+  g.cxGapAt = 0x7fffffff; g.cxGapLen = 0; g.ox0 = ghost; g.ox1 = ghost + lw;
   g.texelX = (float)(1.0 / (double)Wg); g.texelY = (float)(1.0 / (double)H);
   g.Wf = (float)Wg; g.Hf = (float)H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;

@@ -74,7 +74,7 @@ void* hc_create(int W, int H) {
   s->fb.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
   s->initial_T.assign(H + 2, 0.0f); s->sndT.assign(H + 2, 0.0f); s->sndW.assign(H + 2, 0.0f); s->sndV.assign(H + 2, 0.0f);
   Geom& g = s->g;  // as wsb_create (csrc/wsb200.cu), single domain
-  g.Wg = W; g.H = H; g.pitch = W; g.gx0 = 0; g.wrap = 1; g.cx0 = 0; g.cx1 = W;
+  g.Wg = W; g.H = H; g.pitch = W; g.gx0 = 0; g.wrap = 1; g.cx0 = 0; g.cx1 = W; g.cxGapAt = 0x7fffffff; g.cxGapLen = 0; g.ox0 = 0; g.ox1 = W;
   g.texelX = (float)(1.0 / (double)W); g.texelY = (float)(1.0 / (double)H);
   g.Wf = (float)W; g.Hf = (float)H;
   g.ltexelX = 1.0f / g.Wf; g.ltexelY = 1.0f / g.Hf;

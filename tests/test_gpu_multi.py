@@ -1,5 +1,6 @@
-"""2-GPU x-strip run vs the single-GPU run: bit-identical fields (needs >= 2 CUDA devices; on a
-1-GPU box the test is skipped — the decomposition plan itself is covered on CPU by
+"""2/4/8-GPU x-strip runs vs the single-GPU run: bit-identical fields, both ghost-exchange transports
+(needs >= 2 CUDA devices; on a 1-GPU box these are skipped — there tests/test_gpu_strips.py runs the
+same strips with every rank on GPU 0, and the decomposition plan itself is covered on CPU by
 test_oracle_sim.py::test_fake_cluster_strips_bit_identical and test_multi_gloo.py)."""
 import os
 import socket
@@ -12,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, W, H, iters, ret):
+def _worker(rank, world, port, W, H, iters, ret, transport):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -28,7 +29,7 @@ def _worker(rank, world, port, W, H, iters, ret):
     try:
         g, base, water, wall, _ = stress_state(W, H, seed=23)
         g["enablePrecipitation"] = False
-        sim = wsb200.multi.create_distributed(W, H, device=rank, gui_controls=g)
+        sim = wsb200.multi.create_distributed(W, H, device=rank, gui_controls=g, transport=transport)
         sim.upload(base, water, wall, None)
         sim.step(iters)
         S = wsb200.sim
@@ -39,13 +40,15 @@ def _worker(rank, world, port, W, H, iters, ret):
             out[name] = wsb200.multi.gather_strips(full[:, x0:x0 + lw], W)
         if rank == 0:
             np.savez(ret, **out)
+        dist.barrier()  # nobody unmaps a window a neighbour may still be writing into
         sim.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_strips_bit_identical_to_single_gpu(world, tmp_path):
+def test_strips_bit_identical_to_single_gpu(world, transport, tmp_path):
     import torch
     import torch.multiprocessing as mp
 
@@ -59,7 +62,7 @@ def test_strips_bit_identical_to_single_gpu(world, tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ret = str(tmp_path / "out.npz")
-    mp.spawn(_worker, args=(world, port, W, H, iters, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, W, H, iters, ret, transport), nprocs=world, join=True)
     got = np.load(ret)
     g, base, water, wall, _ = stress_state(W, H, seed=23)
     g["enablePrecipitation"] = False

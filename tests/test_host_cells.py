@@ -204,13 +204,11 @@ def test_fused_kernels_on_the_emulator_with_tools_and_airplane(emu, kind, intens
     em.close()
 
 
-@pytest.mark.parametrize("variant", ["shipped", "pairadv"])
 @pytest.mark.parametrize("shape,scale", [((512, 128), 1.0), ((384, 96), 15.0), ((256, 64), 25.0), ((150, 61), 8.0), ((203, 77), 10.0)])
-def test_fused_dry_sweep_on_the_emulator_reproduces_the_oracle(request, shape, scale, variant):
+def test_fused_dry_sweep_on_the_emulator_reproduces_the_oracle(emu, shape, scale):
     """Slow, moderate (near back-trace in every direction) and fast flow (hand-over to the exact
     path), wall blocks in the flow, TMA-staged and register-staged tiles, 64 x 28 tiles on ragged
-    grids; the shipped kernel and the experimental two-cells-per-thread variant (default off)."""
-    emu = request.getfixturevalue("emu" if variant == "shipped" else "emu_pairadv")
+    grids."""
     w, h = shape
     base, water, wall = wsb200.synth.dry_state(w, h, seed=11)
     base[1:, :, 0:2] *= np.float32(scale)

@@ -122,3 +122,28 @@ def test_fake_cluster_strips_bit_identical(n_strips):
             got = o.field(f, b)[:, G:G + lw]
             assert np.array_equal(got, want[:, x0:x0 + lw]), (f, b, x0)
     assert float(np.abs(whole.field(O.FIELD_BASE, 0)[..., :2]).max()) < 1.0
+
+
+@pytest.mark.parametrize("dry", [False, True])
+def test_oracle_window_equals_whole_domain(dry):
+    """The windows the full-size GPU tests compare against (util.oracle_window: a strip of columns with a margin of
+    STRIP_RADIUS columns per iteration, told its global x offset) reproduce the whole-domain oracle run exactly —
+    across the periodic seam too."""
+    from util import oracle_window, window_starts
+
+    W, H, iters = 640, 96, 3
+    if dry:
+        base, water, wall = wsb200.synth.dry_state(W, H, seed=5)
+        base[1:, :, 0:2] *= np.float32(20.0)  # |v| up to ~2.5 cells / iteration
+        g = P.resolve_settings(None)
+    else:
+        g, base, water, wall, _ = stress_state(W, H, seed=31)
+        g["enablePrecipitation"] = False
+    whole = make_oracle(g, base, water, wall, None)
+    (whole.step_dry if dry else whole.step)(iters)
+    want_all = {"base": whole.field(O.FIELD_BASE, 0), "water": whole.field(O.FIELD_WATER, 1), "wall": whole.field(O.FIELD_WALL, 0),
+                "light": whole.light_latest()}
+    for x_first in window_starts(W):
+        got, cols = oracle_window(g, (base, water, wall), W, H, x_first, iters, dry)
+        for name, arr in got.items():
+            assert np.array_equal(arr, want_all[name][:, cols], equal_nan=arr.dtype != np.int8), (name, x_first)

@@ -97,3 +97,38 @@ def ulp_diff(a, b):
     ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
     bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
     return int(np.max(np.abs(ai - bi))) if ai.size else 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Oracle windows: the oracle on a strip of columns of a large grid (tests at BASELINE sizes)
+# ---------------------------------------------------------------------------------------------
+STRIP_OWNED = 40        # columns compared per window
+STRIP_RADIUS = 8        # columns one iteration can reach (3 boundary chain + 1 + ceil|v| <= 4, cf. strips.py)
+
+
+def oracle_window(g, fields, W, H, x_first, iters, dry, fi=None):
+    """Oracle run on global columns [x_first - margin, x_first + STRIP_OWNED + margin) (periodic);
+    returns {name: array[:, STRIP_OWNED, 4]} of the window's owned columns and their global indices."""
+    margin = STRIP_RADIUS * iters + 8
+    cols = np.arange(x_first - margin, x_first + STRIP_OWNED + margin) % W
+    base, water, wall = (f[:, cols] for f in fields)
+    ora = O.OracleSim(len(cols), H, 0, global_width=W, x0=x_first - margin)
+    ora.upload(base, water, wall, None)
+    ora.set_params(P.derive_params(g))
+    ora.set_frame_inputs(fi if fi is not None else P.frame_inputs(g))
+    ora.set_profiles(P.initial_T_profile(H, g))
+    (ora.step_dry if dry else ora.step)(iters)
+    own = slice(margin, margin + STRIP_OWNED)
+    out = {"base": ora.field(O.FIELD_BASE, 0)[:, own]}
+    if not dry:
+        out["water"] = ora.field(O.FIELD_WATER, 1)[:, own]
+        out["wall"] = ora.field(O.FIELD_WALL, 0)[:, own]
+        out["light"] = ora.light_latest()[:, own]
+    ora.close()
+    return out, cols[own]
+
+
+def window_starts(W):
+    # the periodic seam (columns W-20 .. W-1, 0 .. 19), the middle (x = W/2 straddles a power of two:
+    # fp32 spacing of fragCoord doubles there), the last columns, and an arbitrary tile-straddling one
+    return [W - 20, W // 2 - 20, W - STRIP_OWNED, (W // 3) | 1]
