@@ -189,19 +189,25 @@ __device__ __forceinline__ unsigned* flag_of(unsigned char* arena, unsigned long
   return reinterpret_cast<unsigned*>(arena + pb * kArenaSlots) + f * kFlagStride;
 }
 
+// One thread: tell both neighbours that this rank has finished reading the ghost columns of exchange seq-1
+// (everything that reads them precedes this kernel in stream order), then wait for the same word from them.
+// A kernel of its own so that nothing bigger than one warp ever sits on an SM while it waits (a spinning
+// many-block kernel displaces a resident CTA of the advection kernel on every SM it occupies: measured
+// +0.2 ms per iteration at 2 GPUs, profiles/r3_multi_gpu.md).
+__global__ void k_ghosts_free(const __grid_constant__ PushArgs a) {
+  unsigned* myFlags = flag_of(a.mine, a.pbMine, 0);
+  st_release_sys(flag_of(a.left, a.pbLeft, kFlagFreeR), a.seq);
+  st_release_sys(flag_of(a.right, a.pbRight, kFlagFreeL), a.seq);
+  wait_flag(myFlags + kFlagFreeL * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
+  wait_flag(myFlags + kFlagFreeR * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
+}
+
+// Grid-stride copy of this rank's outermost owned columns into the neighbours' ghost columns; the last block
+// to finish raises the neighbours' data flags.
 __global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ PushArgs a) {
   unsigned* myFlags = flag_of(a.mine, a.pbMine, 0);
-  if (threadIdx.x == 0) {
-    // everything of this rank that reads the ghost columns of exchange seq-1 precedes this kernel in stream order
-    st_release_sys(flag_of(a.left, a.pbLeft, kFlagFreeR), a.seq);
-    st_release_sys(flag_of(a.right, a.pbRight, kFlagFreeL), a.seq);
-    wait_flag(myFlags + kFlagFreeL * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
-    wait_flag(myFlags + kFlagFreeR * kFlagStride, a.seq, myFlags + kFlagErr * kFlagStride, a.spinNs);
-  }
-  __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = a.H * 2;  // (row, column quad)
-  if (t < per * a.n) {
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per * a.n; t += gridDim.x * blockDim.x) {
     const int k = t / per, r = t - k * per;
     const int y = r >> 1, q = (r & 1) * 4;
     const unsigned long long sl = (unsigned long long)a.slot[k];
@@ -424,7 +430,9 @@ int exchange(wsb_sim* s, const XPlanes& xp, bool afterEdge) {
     for (int k = 0; k < hp.n; k++) a.slot[k] = xp.slot[k];
     a.seq = ++s->xseq;
     a.spinNs = s->spin_ns;
-    const int threads = 256, blocks = (hp.n * s->H * 2 + threads - 1) / threads;
+    k_ghosts_free<<<1, 1, 0, cs>>>(a);
+    LAUNCHED("k_ghosts_free");
+    const int threads = 256, blocks = std::min(74, (hp.n * s->H * 2 + threads - 1) / threads);  // short-lived, half an SM wave
     k_push_ghosts<<<blocks, threads, 0, cs>>>(a);
     LAUNCHED("k_push_ghosts");
     CK(cudaEventRecord(s->evPush, cs));
@@ -968,7 +976,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
        // synchronise the context — behind a neighbour's spinning k_push_ghosts / k_wait_ghosts that would stall
        // (several strips in one process: deadlock until the bounded wait runs out).
       cudaFuncAttributes fa;
-      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_push_ghosts,
+      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_push_ghosts, (const void*)k_ghosts_free,
                            (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation,
                            (const void*)k_latch, (const void*)k_texels_to_planes, (const void*)k_planes_to_texels, (const void*)k_pressure_rect,
                            (const void*)k_gather_points};

@@ -60,9 +60,28 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
     if transport == "nccl":
         cid = broadcast_comm_id(comm_id_create, group)
         return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
-    sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=None, gui_controls=gui_controls, **kw)
-    connect_ring(sim, group)
-    return sim
+    # peer transport; if any rank cannot map its neighbours (no peer access between the devices, IPC disabled in a
+    # container) EVERY rank falls back to the NCCL transport — loudly
+    sim, err = None, None
+    try:
+        sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=None, gui_controls=gui_controls, **kw)
+        connect_ring(sim, group)
+    except Exception as e:  # noqa: BLE001 — collected and agreed on below
+        err = repr(e)
+    errs = [None] * n
+    dist.all_gather_object(errs, err, group=group)
+    if all(e is None for e in errs):
+        return sim
+    if sim is not None:
+        sim.close()
+    if os.environ.get("WSB_EXCHANGE") == "peer":  # explicitly requested: do not hide the failure
+        raise RuntimeError(f"peer-memory ghost exchange unavailable: {[e for e in errs if e][0]}")
+    if r == 0:
+        import warnings
+
+        warnings.warn(f"wsb200: peer-memory ghost exchange unavailable ({[e for e in errs if e][0]}); using ncclSend/ncclRecv")
+    cid = broadcast_comm_id(comm_id_create, group)
+    return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
 
 
 def gather_strips(local: np.ndarray, width: int, group=None):

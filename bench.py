@@ -12,8 +12,16 @@ grid: pressure, velocity, curl, vorticity, boundary, advection (+ condensation),
 GPU at N = 1).  The total grid is fixed, so scaling is "strong".  Rank 0 prints ONE JSON line.
 
 Timing: CUDA events on the simulation's own stream inside libwsb200 (wsb_last_step_ms) around
-exactly K iterations, bracketed by barrier + synchronize, max over ranks.  Inputs are GiB-sized
-planes (>> 126 MB L2), so no L2 flush is needed between iterations.
+exactly K iterations, bracketed by barrier + synchronize, max over ranks (`value`); `sustained` is
+the median over SUSTAINED_BATCHES further batches of K iterations each, timed the same way.  Inputs
+are GiB-sized planes (>> 126 MB L2), so no L2 flush is needed between iterations.
+
+At N = 1 the line also carries every other BASELINE.json config as its own object with `roofline`
+and `clocks`: `dry_sweep` (k_fused_dry at the headline grid: the >= 70 % target), `config2_dry_4096x1024`,
+`config3_full_8192x2048`, `with_particles` (config 4: + 1 M droplets) and `with_particles_ref_count`
+(the W*H/25 = 2.68 M droplets the reference itself would allocate, app.js:452,1282).
+At N > 1 rank 0 re-runs the end-to-end leg on ONE GPU and compares every strip bit for bit
+(`config.bit_identical_to_1gpu`); a flow beyond the strips' ghost budget fails the run (rc != 0).
 """
 from __future__ import annotations
 
@@ -40,6 +48,8 @@ B_ALG = {
     "k_fused_dry": 36,   # R base 16 + wall 4; W base 16
 }
 PREWARM_ITERS = 150      # untimed, before the W warm-up steps
+SUSTAINED_BATCHES = 10   # further timed batches of K steps (median reported beside the single batch)
+E2E_LONG_K = 200         # second end-to-end figure: PCIe traffic amortised over 200 steps (N = 1)
 B_ALG_STEP_FULL = 104    # every live field read once + written once per iteration
 
 
@@ -113,6 +123,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm)}
 
 
+TRAFFIC_SOURCE = "profiles/ncu_traffic.json (static: ncu --set full capture of this kernel at this grid, not measured in this run)"
+
+
 def _ncu_traffic(kernel: str, W: int, H: int, world: int):
     """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json),
     only when the capture was taken at this grid on one GPU; otherwise null."""
@@ -166,6 +179,8 @@ def cpu_baseline(budget_s: float = 12.0):
 
     cores = O.lib().oracle_get_threads()
     return {"value": cols * h * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "same_config": False,
+            "workload": f"per-cell rate extrapolated from a {cols}x{h} slab = 1/{GRID_W // cols} of the 16384x4096 grid",
             "sample": f"{cols}x{h} periodic slab of the bench state (full physics, no particles), {n} iterations, OpenMP over rows; "
                       "CPU restatement of the reference shaders (oracle/wsb_oracle.cpp) — the reference itself (GLSL under a browser) cannot run here"}
 
@@ -189,7 +204,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "full physics 16384x4096 fp32, no particles (CPU: bounded slab sample)", "grid": [GRID_W, GRID_H]},
+            "config": {"workload": f"full physics 16384x4096 fp32, no particles — CPU arm: per-cell rate extrapolated from a {cols}x{h} slab = 1/{GRID_W // cols} of the grid per step",
+                       "grid": [GRID_W, GRID_H], "same_config": False},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -227,6 +243,34 @@ def _pinned(shape, dtype):
     return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
 
 
+def _digest(*arrays) -> str:
+    import hashlib
+
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def _timed_batches(sim, step, K, n, world, device):
+    """n further batches of K steps, each bracketed like the headline batch; ms per step of each (max over ranks)."""
+    out = []
+    for _ in range(n):
+        _barrier(world)
+        step(K)
+        sim.sync()
+        out.append(_max_over_ranks(sim.last_step_ms(), world, device) / K)
+    return out
+
+
+def _roofline(kernel, per_launch_ms, cells, peak, peak_src, W, H, world):
+    achieved = B_ALG[kernel] * cells / (per_launch_ms * 1e-3) / 1e9
+    t = _ncu_traffic(kernel, W, H, world)
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": t, "traffic_source": TRAFFIC_SOURCE if t is not None else None, "peak_source": peak_src,
+            "alg_bytes_per_cell": B_ALG[kernel], "avg_launch_ms": per_launch_ms}
+
+
 def run_ours(args):
     import torch
 
@@ -247,12 +291,13 @@ def run_ours(args):
     W, H = args.width, args.height
     K, Wm = args.steps, max(args.warmup, 3)
     peak, peak_src = _peaks()
+    transport = os.environ.get("WSB_EXCHANGE", "peer")
 
     g = P.resolve_settings(None)
     g["enablePrecipitation"] = False
     g["dayNightCycle"] = False
     g["sunAngle"] = 60.0
-    sim = wsb200.multi.create_distributed(W, H, device=local_rank, gui_controls=g)
+    sim = wsb200.multi.create_distributed(W, H, device=local_rank, gui_controls=g, transport=transport)
     x0, lw, gh = sim.layout()
     cols = sim.padded_columns()
     base, water, wall, _ = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=False, cols=cols)
@@ -280,55 +325,121 @@ def run_ours(args):
     _barrier(world)
     clocks = sampler.result()
     launches = sim.launch_count - launches0
-    kt = {name: sim.kernel_time_ms(k) for name, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("halo", S.KERNEL_HALO))}
+    kt = {name: sim.kernel_time_ms(k) for name, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("halo", S.KERNEL_HALO),
+                                                       ("ghost_wait", S.KERNEL_WAIT))}
+    ms_mine = ms
     ms = _max_over_ranks(ms, world, device)
     value = W * H * K / (ms * 1e-3)
     vmax = sim.max_velocity
 
-    # roofline of the dominant kernel (this rank's strip; cells include the ghost columns it computes)
+    # roofline of the dominant kernel (this rank's strip; cells include the ghost columns it computes).
+    # On a strip a kernel class is several launches per iteration (interior + edge tile columns): per-iteration time.
     local_cells = (lw + 2 * gh) * H
     dom = max(("k_fused_pvb", "k_fused_adv"), key=lambda n: kt[n][0])
-    dom_ms = kt[dom][0] / max(kt[dom][1], 1)
-    achieved = B_ALG[dom] * local_cells / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": _ncu_traffic(dom, W, H, world), "peak_source": peak_src, "alg_bytes_per_cell": B_ALG[dom], "avg_launch_ms": dom_ms,
-                "kernels_ms_per_step": {n: (t / max(c, 1)) for n, (t, c) in kt.items()},
-                "step_frac_of_104B_roofline": (B_ALG_STEP_FULL * W * H / world / (ms / K * 1e-3) / 1e9) / peak}
+    dom_ms = kt[dom][0] / K
+    roofline = _roofline(dom, dom_ms, local_cells, peak, peak_src, W, H, world)
+    roofline["kernels_ms_per_step"] = {n: t / K for n, (t, c) in kt.items()}
+    roofline["launches_per_step"] = {n: c / K for n, (t, c) in kt.items()}
+    roofline["step_frac_of_104B_roofline"] = (B_ALG_STEP_FULL * W * H / world / (ms / K * 1e-3) / 1e9) / peak
+    if world > 1:  # every rank's own view: strips run in loose lock-step, the slowest one sets the pace
+        import torch.distributed as dist
+
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": ms_mine / K, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
+                                          **{n: round(t / K, 4) for n, (t, c) in kt.items()}})
+        roofline["per_rank"] = per_rank
+
+    # ---- sustained: the median of further batches of K steps ---------------------------------
+    sus_sampler = ClockSampler(local_rank)
+    sus_sampler.start()
+    batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES, world, device)
+    sus_clocks = sus_sampler.result()
+    med = float(np.median(batches))
+    sustained = {"batches": len(batches), "steps_per_batch": K, "ms_per_step_median": med, "ms_per_step_min": min(batches), "ms_per_step_max": max(batches),
+                 "value_median": W * H / (med * 1e-3), "unit": UNIT, "clocks": sus_clocks}
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the public API ------------
     ob, ow, ol = _pinned((H, lw, 4), np.float32), _pinned((H, lw, 4), np.float32), _pinned((H, lw, 4), np.int8)
     fi = sim.frame_inputs
-    _barrier(world)
-    t0 = time.perf_counter()
-    sim.upload_local(hb, hw, hl)                      # loadData -> textures (pinned host -> HBM)
-    for _ in range(K):
-        sim.set_frame_inputs(fi)                      # per-frame uniforms
-        sim.step(1)
-    sim.read_pixels(S.FIELD_BASE, x0, 0, lw, H, out=ob)   # prepareDownload: frameBuff_0 readback
-    sim.read_pixels(S.FIELD_WATER, x0, 0, lw, H, out=ow)
-    sim.read_pixels(S.FIELD_WALL, x0, 0, lw, H, out=ol)
-    torch.cuda.synchronize()
-    e2e_s = _max_over_ranks(time.perf_counter() - t0, world, device)
-    h2d = (hb.nbytes + hw.nbytes + hl.nbytes) * world / K + 56
-    d2h = (ob.nbytes + ow.nbytes + ol.nbytes) * world / K
-    e2e = {"value": W * H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "what": f"upload of the state from pinned host memory + {K} x (set_frame_inputs + step(1)) + readback of base/water/wall to pinned host, "
-                   "host wall clock, bytes amortised over the K steps"}
-    finite = bool(np.isfinite(ob).all())
-    sim.close()
 
+    def e2e_run(k):
+        _barrier(world)
+        t0 = time.perf_counter()
+        sim.upload_local(hb, hw, hl)                      # loadData -> textures (pinned host -> HBM)
+        for _ in range(k):
+            sim.set_frame_inputs(fi)                      # per-frame uniforms
+            sim.step(1)
+        sim.read_pixels(S.FIELD_BASE, x0, 0, lw, H, out=ob)   # prepareDownload: frameBuff_0 readback
+        sim.read_pixels(S.FIELD_WATER, x0, 0, lw, H, out=ow)
+        sim.read_pixels(S.FIELD_WALL, x0, 0, lw, H, out=ol)
+        torch.cuda.synchronize()
+        return _max_over_ranks(time.perf_counter() - t0, world, device)
+
+    e2e_s = e2e_run(K)
+    h2d_total = (hb.nbytes + hw.nbytes + hl.nbytes) * world
+    d2h_total = (ob.nbytes + ow.nbytes + ol.nbytes) * world
+    e2e = {"value": W * H * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d_total / K + 56, "d2h_bytes_per_step": d2h_total / K, "steps": K,
+           "seconds": e2e_s,
+           "what": f"upload of the state from pinned host memory + {K} x (set_frame_inputs + step(1)) + readback of base/water/wall to pinned host, "
+                   f"host wall clock; the {h2d_total / 1e9:.2f} GB up + {d2h_total / 1e9:.2f} GB down are amortised over these {K} steps, so the figure moves with K"}
+    finite = bool(np.isfinite(ob).all())
+
+    # ---- N > 1: the strips against ONE GPU, bit for bit (same upload + K steps as the end-to-end leg) ----
+    ident = None
+    if world > 1:
+        import torch.distributed as dist
+
+        light = sim.read_pixels(S.FIELD_LIGHT, x0, 0, lw, H, view=S.VIEW_LATEST)
+        mine = {"x0": x0, "lw": lw, "base": _digest(ob), "water": _digest(ow), "wall": _digest(ol), "light": _digest(light)}
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank == 0:
+            fb_, fw_, fl_, _ = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=False)
+            one = wsb200.Simulation(W, H, 0, device=local_rank, gui_controls=g)
+            one.upload(fb_, fw_, fl_)
+            del fb_, fw_, fl_
+            for _ in range(K):
+                one.set_frame_inputs(fi)
+                one.step(1)
+            full = {"base": one.read_pixels(S.FIELD_BASE), "water": one.read_pixels(S.FIELD_WATER), "wall": one.read_pixels(S.FIELD_WALL),
+                    "light": one.read_pixels(S.FIELD_LIGHT, view=S.VIEW_LATEST)}
+            one.close()
+            bad = [f"rank {r}: {name}" for r, p_ in enumerate(parts) for name in ("base", "water", "wall", "light")
+                   if _digest(full[name][:, p_["x0"]:p_["x0"] + p_["lw"]]) != p_[name]]
+            ident = {"ok": not bad, "mismatches": bad, "what": f"sha1 of every rank's own columns (base, water, wall, light) after upload + {K} iterations "
+                                                               "vs the same run on one GPU (rank 0's device)"}
+            del full
+    else:
+        e2e_long_s = e2e_run(E2E_LONG_K)
+        e2e["k200"] = {"value": W * H * E2E_LONG_K / e2e_long_s, "steps": E2E_LONG_K, "seconds": e2e_long_s,
+                       "h2d_bytes_per_step": h2d_total / E2E_LONG_K + 56, "d2h_bytes_per_step": d2h_total / E2E_LONG_K}
+    sim.close()
+    del hb, hw, hl, ob, ow, ol
+
+    partition = "single GPU"
+    if world > 1:
+        how = ("k_push_ghosts: edge columns stored straight into the neighbours' ghost columns over NVLink (cudaIpc windows), sequence flags"
+               if transport == "peer" else "pack + ncclSend/ncclRecv + unpack")
+        partition = f"{world} x-strip(s) of {lw} columns, ghost {gh}, one ring exchange per iteration ({how})"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"full physics {W}x{H} fp32 (pressure+velocity+vorticity+boundary+advection+condensation+lighting), no particles",
-                       "grid": [W, H], "partition": f"{world} x-strip(s) of {lw} columns, ghost {gh}, one NCCL ring exchange per iteration" if world > 1 else "single GPU",
+                       "grid": [W, H], "partition": partition, "transport": transport if world > 1 else None,
                        "schedule": "fused: k_fused_pvb + k_fused_adv per iteration (TMA-staged channel planes)", "prewarm": f"{PREWARM_ITERS} untimed iterations before the W warm-up steps (SM clock ramp-up after host-side state generation)", "l2": "no flush: every plane is >= 256 MiB, far larger than the 126 MB L2",
                        "max_abs_velocity_cells_per_iter": vmax, "state_finite": finite},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+            "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}
+    if ident is not None:
+        line["config"]["bit_identical_to_1gpu"] = ident["ok"]
+        line["config"]["bit_identical_check"] = ident
 
-    if world == 1 and rank == 0:
-        line["dry_sweep"] = dry_sweep_leg(W, H, K, Wm, peak, local_rank, prewarm=not args.no_prewarm)
-        if args.particles:
-            line["with_particles"] = particles_leg(W, H, K, Wm, local_rank)
+    if world == 1 and rank == 0 and not args.headline_only:
+        pre = not args.no_prewarm
+        line["dry_sweep"] = dry_sweep_leg(W, H, K, Wm, peak, peak_src, local_rank, prewarm=pre)
+        line["config2_dry_4096x1024"] = dry_sweep_leg(4096, 1024, K, Wm, peak, peak_src, local_rank, prewarm=pre,
+                                                      note="working set (4 base planes x 2 copies + wall = 151 MB) is L2-sized (126 MB L2): the HBM roofline fraction is not meaningful here (SURVEY 8d)")
+        line["config3_full_8192x2048"] = full_leg(8192, 2048, K, Wm, peak, peak_src, local_rank, prewarm=pre)
+        line["with_particles"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, 1_000_000)
+        line["with_particles_ref_count"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, W * H // 25)
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
     if world > 1:
@@ -338,11 +449,13 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
+        if ident is not None and not ident["ok"]:
+            raise SystemExit("bench.py: strips differ from the single-GPU run: " + ", ".join(ident["mismatches"]))
 
 
-def dry_sweep_leg(W, H, K, Wm, peak, device_index, prewarm=True):
-    """The fused pressure+velocity+advection sweep (k_fused_dry) at the same grid: the kernel the
-    >= 70 % HBM-roofline target of BASELINE.json is stated on."""
+def dry_sweep_leg(W, H, K, Wm, peak, peak_src, device_index, prewarm=True, note=None):
+    """The fused pressure+velocity+advection sweep (k_fused_dry): at the headline grid the kernel the
+    >= 70 % HBM-roofline target of BASELINE.json is stated on; at 4096 x 1024 BASELINE config 2."""
     import wsb200
 
     S, P = wsb200.sim, wsb200.params
@@ -365,39 +478,93 @@ def dry_sweep_leg(W, H, K, Wm, peak, device_index, prewarm=True):
     ms = sim.last_step_ms()
     t, c = sim.kernel_time_ms(S.KERNEL_DRY)
     per = t / max(c, 1)
-    achieved = B_ALG["k_fused_dry"] * W * H / (per * 1e-3) / 1e9
-    out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K,
-           "roofline": {"bound": "hbm", "kernel": "k_fused_dry", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": _ncu_traffic("k_fused_dry", W, H, 1), "alg_bytes_per_cell": B_ALG["k_fused_dry"], "avg_launch_ms": per},
+    batches = _timed_batches(sim, sim.step_dry, K, SUSTAINED_BATCHES, 1, None)
+    out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "grid": [W, H],
+           "workload": "dry sweep: pressure(prev) + velocity + semi-Lagrangian advection of the base field, one kernel per iteration",
+           "roofline": _roofline("k_fused_dry", per, W * H, peak, peak_src, W, H, 1),
+           "sustained_ms_per_step_median": float(np.median(batches)),
            "max_abs_velocity_cells_per_iter": sim.max_velocity, "clocks": clocks}
+    if note:
+        out["note"] = note
     sim.close()
     return out
 
 
-def particles_leg(W, H, K, Wm, device_index):
-    """BASELINE config 4: full physics + 1 M precipitation particles on one GPU."""
+def full_leg(W, H, K, Wm, peak, peak_src, device_index, prewarm=True):
+    """BASELINE config 3: full physics (no particles) at 8192 x 2048 on one GPU."""
+    import wsb200
+
+    S, P = wsb200.sim, wsb200.params
+    g = P.resolve_settings(None)
+    g["enablePrecipitation"] = False
+    g["dayNightCycle"] = False
+    g["sunAngle"] = 60.0
+    sim = wsb200.Simulation(W, H, 0, device=device_index, gui_controls=g)
+    base, water, wall, _ = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=False)
+    sim.upload(base, water, wall)
+    del base, water, wall
+    sim.set_profiling(True)
+    if prewarm:
+        sim.step(4 * PREWARM_ITERS)
+        sim.sync()
+    sim.step(Wm)
+    sim.sync()
+    sampler = ClockSampler(device_index)
+    sampler.start()
+    sim.step(K)
+    sim.sync()
+    clocks = sampler.result()
+    ms = sim.last_step_ms()
+    kt = {n: sim.kernel_time_ms(k) for n, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV))}
+    dom = max(kt, key=lambda n: kt[n][0])
+    batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES, 1, None)
+    rl = _roofline(dom, kt[dom][0] / max(kt[dom][1], 1), W * H, peak, peak_src, W, H, 1)
+    rl["kernels_ms_per_step"] = {n: t / max(c, 1) for n, (t, c) in kt.items()}
+    rl["step_frac_of_104B_roofline"] = (B_ALG_STEP_FULL * W * H / (ms / K * 1e-3) / 1e9) / peak
+    out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "grid": [W, H],
+           "workload": "full physics (pressure+velocity+vorticity+boundary+advection+condensation+lighting), no particles",
+           "roofline": rl, "sustained_ms_per_step_median": float(np.median(batches)), "clocks": clocks,
+           "note": "every plane is 64 MiB: the 25 planes of one iteration (1.6 GB) are far beyond the 126 MB L2"}
+    sim.close()
+    return out
+
+
+def particles_leg(W, H, K, Wm, peak, peak_src, device_index, nd):
+    """BASELINE config 4: full physics + precipitation particles on one GPU (1 M droplets as named by the config; and the
+    W*H/25 droplets the reference itself allocates for this grid, app.js:452,1282)."""
     import wsb200
 
     S, P = wsb200.sim, wsb200.params
     g = P.resolve_settings(None)
     g["dayNightCycle"] = False
     g["sunAngle"] = 60.0
-    nd = 1_000_000
     sim = wsb200.Simulation(W, H, nd, device=device_index, gui_controls=g)
     base, water, wall, drops = wsb200.synth.full_state(W, H, seed=7, g=g, with_droplets=True, n_droplets=nd)
     wsb200.synth.add_clouds(base, water, wall, n_blobs=96, seed=5)  # something to rain from
     sim.upload(base, water, wall, drops)
     del base, water, wall
     sim.set_profiling(True)
-    sim.step(max(Wm, 30))  # spin-up: the first iterations spawn the bulk of the droplets
+    sim.step(max(Wm, 30) + PREWARM_ITERS)  # spin-up: the first iterations spawn the bulk of the droplets
     sim.sync()
+    sampler = ClockSampler(device_index)
+    sampler.start()
     sim.step(K)
     sim.sync()
+    clocks = sampler.result()
     ms = sim.last_step_ms()
     kt = {n: sim.kernel_time_ms(k) for n, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("k_precipitation", S.KERNEL_PRECIP))}
     d = sim.read_droplets()
-    out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "n_droplets": nd, "active_droplets": int((d[:, 2] >= 0).sum()),
-           "kernels_ms_per_step": {n: t / max(c, 1) for n, (t, c) in kt.items()}}
+    dom = max(("k_fused_pvb", "k_fused_adv"), key=lambda n: kt[n][0])
+    rl = _roofline(dom, kt[dom][0] / max(kt[dom][1], 1), W * H, peak, peak_src, W, H, 1)
+    if dom == "k_fused_pvb":  # after a particle pass the boundary kernel also reads feedback (16 B) + deposition (8 B)
+        rl["alg_bytes_per_cell"] = B_ALG[dom] + 24
+        rl["achieved"] = rl["alg_bytes_per_cell"] * W * H / (rl["avg_launch_ms"] * 1e-3) / 1e9
+        rl["frac"] = rl["achieved"] / peak
+    rl["traffic"], rl["traffic_source"] = None, None
+    rl["kernels_ms_per_step"] = {n: t / max(c, 1) for n, (t, c) in kt.items()}
+    out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "grid": [W, H], "n_droplets": nd,
+           "active_droplets": int((d[:, 2] >= 0).sum()), "workload": "full physics + precipitation particles (k_precipitation + k_latch per iteration)",
+           "roofline": rl, "clocks": clocks}
     sim.close()
     return out
 
@@ -410,7 +577,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=GRID_W)
     ap.add_argument("--height", type=int, default=GRID_H)
-    ap.add_argument("--particles", action="store_true", help="also run BASELINE config 4 (1 M droplets) at N=1")
+    ap.add_argument("--headline-only", action="store_true", help="N=1: skip the extra legs (dry sweep, configs 2-4, cpu baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-prewarm", action="store_true", help="skip the clock ramp-up iterations (profiler runs)")
     args = ap.parse_args()
