@@ -330,7 +330,7 @@ struct wsb_sim {
   int pitchL = 0, pitchR = 0, lwL = 0;
   unsigned xseq = 0, pending_seq = 0;       // exchanges issued / the one in flight
   unsigned long long spin_ns = kSpinLimitNs;
-  cudaEvent_t evEdge = nullptr, evPush = nullptr;
+  cudaEvent_t evEdge = nullptr, evPush = nullptr, evPvbI = nullptr, evPvbE = nullptr, evAdvI = nullptr;
   bool push_pending = false;                // a k_push_ghosts is reading this rank's edge columns
   int pvbInnerEnd = 0, advEdgeStart = 0;    // tile-column split of the strip (local columns)
 };
@@ -404,43 +404,43 @@ void add_wall(XPlanes& x, const wsb_sim* s, int k) {
   x.hp.p[x.hp.n++] = s->wall[k];
 }
 
-// Ghost-column exchange on comm_stream.  It starts once `after` (an event on the compute stream:
-// the iteration's edge tiles, or everything enqueued so far) has fired and stays in flight
-// (exch_pending) until join_exchange() orders the compute stream behind it — the interior tiles
-// of the advection kernel and of the next iteration's boundary kernel run beside it.
-int exchange(wsb_sim* s, const XPlanes& xp, bool afterEdge) {
+// Peer transport: on the communication stream, after whatever the caller has ordered there — the handshake kernel,
+// then the copy of this rank's outermost owned columns into the neighbours' ghost columns.
+int push_ghosts(wsb_sim* s, const XPlanes& xp) {
+  cudaStream_t cs = s->comm_stream;
+  const HaloPlanes& hp = xp.hp;
+  ProfScope prof(s, WSB_KERNEL_HALO, cs);
+  PushArgs a{};
+  a.mine = s->arena; a.left = s->peerL; a.right = s->peerR;
+  a.pbMine = s->plane_bytes; a.pbLeft = s->pbL; a.pbRight = s->pbR;
+  a.pitchMine = s->pitch; a.pitchLeft = s->pitchL; a.pitchRight = s->pitchR;
+  a.lw = s->lw; a.lwLeft = s->lwL; a.H = s->H;
+  a.vec = (s->pitch % 4 == 0 && s->pitchL % 4 == 0 && s->pitchR % 4 == 0 && s->lw % 4 == 0 && s->lwL % 4 == 0) ? 1 : 0;
+  a.n = hp.n;
+  for (int k = 0; k < hp.n; k++) a.slot[k] = xp.slot[k];
+  a.seq = ++s->xseq;
+  a.spinNs = s->spin_ns;
+  k_ghosts_free<<<1, 1, 0, cs>>>(a);
+  LAUNCHED("k_ghosts_free");
+  const int threads = 256, blocks = std::min(74, (hp.n * s->H * 2 + threads - 1) / threads);  // short-lived, half an SM wave
+  k_push_ghosts<<<blocks, threads, 0, cs>>>(a);
+  LAUNCHED("k_push_ghosts");
+  CK(cudaEventRecord(s->evPush, cs));
+  s->pending_seq = a.seq;
+  s->push_pending = true;
+  s->exch_pending = true;
+  return 0;
+}
+
+// Ghost-column exchange on comm_stream, ordered after everything enqueued on the compute stream so
+// far.  It stays in flight (exch_pending) until join_exchange() orders the compute stream behind it.
+int exchange(wsb_sim* s, const XPlanes& xp) {
   if (s->cfg.n_ranks <= 1) return 0;
   cudaStream_t cs = s->comm_stream;
   const HaloPlanes& hp = xp.hp;
-  if (afterEdge) {
-    CK(cudaStreamWaitEvent(cs, s->evEdge, 0));
-  } else {
-    CK(cudaEventRecord(s->evCompute, s->stream));
-    CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
-  }
-  if (s->peer_mode) {
-    ProfScope prof(s, WSB_KERNEL_HALO, cs);
-    PushArgs a{};
-    a.mine = s->arena; a.left = s->peerL; a.right = s->peerR;
-    a.pbMine = s->plane_bytes; a.pbLeft = s->pbL; a.pbRight = s->pbR;
-    a.pitchMine = s->pitch; a.pitchLeft = s->pitchL; a.pitchRight = s->pitchR;
-    a.lw = s->lw; a.lwLeft = s->lwL; a.H = s->H;
-    a.vec = (s->pitch % 4 == 0 && s->pitchL % 4 == 0 && s->pitchR % 4 == 0 && s->lw % 4 == 0 && s->lwL % 4 == 0) ? 1 : 0;
-    a.n = hp.n;
-    for (int k = 0; k < hp.n; k++) a.slot[k] = xp.slot[k];
-    a.seq = ++s->xseq;
-    a.spinNs = s->spin_ns;
-    k_ghosts_free<<<1, 1, 0, cs>>>(a);
-    LAUNCHED("k_ghosts_free");
-    const int threads = 256, blocks = std::min(74, (hp.n * s->H * 2 + threads - 1) / threads);  // short-lived, half an SM wave
-    k_push_ghosts<<<blocks, threads, 0, cs>>>(a);
-    LAUNCHED("k_push_ghosts");
-    CK(cudaEventRecord(s->evPush, cs));
-    s->pending_seq = a.seq;
-    s->push_pending = true;
-    s->exch_pending = true;
-    return 0;
-  }
+  CK(cudaEventRecord(s->evCompute, s->stream));
+  CK(cudaStreamWaitEvent(cs, s->evCompute, 0));
+  if (s->peer_mode) return push_ghosts(s, xp);
   if (!s->comm) return fail("no ghost-exchange transport: call wsb_connect_peers (or pass an NCCL comm_id to wsb_create) before stepping a strip");
   {
     ProfScope prof(s, WSB_KERNEL_HALO, cs);
@@ -469,13 +469,18 @@ int exchange(wsb_sim* s, const XPlanes& xp, bool afterEdge) {
   s->exch_pending = true;
   return 0;
 }
+// the neighbours' columns of the exchange in flight have arrived: one-thread kernel on stream `st`
+int wait_ghosts(wsb_sim* s, cudaStream_t st) {
+  ProfScope prof(s, WSB_KERNEL_WAIT, st);
+  k_wait_ghosts<<<1, 1, 0, st>>>(reinterpret_cast<unsigned*>(s->arena + s->plane_bytes * kArenaSlots), s->pending_seq, s->spin_ns);
+  LAUNCHED("k_wait_ghosts");
+  return 0;
+}
 // the compute stream may touch the ghost columns again: the neighbours' data of the exchange in flight has arrived
 int join_exchange(wsb_sim* s) {
   if (s->exch_pending) {
     if (s->peer_mode) {
-      ProfScope prof(s, WSB_KERNEL_WAIT);
-      k_wait_ghosts<<<1, 1, 0, s->stream>>>(reinterpret_cast<unsigned*>(s->arena + s->plane_bytes * kArenaSlots), s->pending_seq, s->spin_ns);
-      LAUNCHED("k_wait_ghosts");
+      if (wait_ghosts(s, s->stream)) return 1;
     } else {
       CK(cudaStreamWaitEvent(s->stream, s->evExch, 0));
     }
@@ -581,89 +586,137 @@ int ref_iteration(wsb_sim* s) {
 
 // --- fused schedule --------------------------------------------------------------------------
 
+// tile columns [cx0, cx1) minus [gapAt, gapAt + gapLen) of one fused kernel on stream `st`
+constexpr int kNoGap = 0x7fffffff;
+int launch_pvb(wsb_sim* s, cudaStream_t st, int cx0, int cx1, int gapAt, int gapLen) {
+  GlobalCtx c = make_ctx(s, 1, 1, 1, 0);
+  TileMaps<11> maps;
+  for (int k = 0; k < 4; k++) {
+    maps.m[k] = s->base[1].map3[k];
+    maps.m[5 + k] = s->water[1].map0[k];
+  }
+  maps.m[4] = s->wallMap3[1];
+  maps.m[9] = s->light[0].map0[0];   // SUNLIGHT
+  maps.m[10] = s->light[0].map0[1];  // NET_HEATING
+  c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+  k_fused_pvb<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, st>>>(
+      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
+      s->base[0].p, s->water[0].p, s->wall[0]);
+  return check_launch(s, "k_fused_pvb");
+}
+int launch_adv(wsb_sim* s, cudaStream_t st, int src, int dst, int cx0, int cx1, int gapAt, int gapLen) {
+  TileMaps<12> maps;
+  for (int k = 0; k < 4; k++) {
+    maps.m[k] = s->base[0].map2[k];
+    maps.m[4 + k] = s->water[0].map2[k];
+  }
+  maps.m[8] = s->wallMap2[0];
+  maps.m[9] = s->light[src].map2[0];   // SUNLIGHT
+  maps.m[10] = s->light[src].map2[2];  // IR_DOWN
+  maps.m[11] = s->light[src].map2[3];  // IR_UP
+  GlobalCtx c = make_ctx(s, 0, 0, 0, src);
+  c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
+  k_fused_adv<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem2, st>>>(
+      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->sndT, s->sndW, s->sndV, s->base[1].p, s->water[1].p, s->wall[1],
+      s->light[dst].p, s->maxv);
+  return check_launch(s, "k_fused_adv");
+}
+void strip_exchange_planes(const wsb_sim* s, int dst, XPlanes& xp) {
+  add_planes(xp, s->base[1]);
+  add_planes(xp, s->water[1]);
+  add_wall(xp, s, 1);
+  add_planes(xp, s->light[dst]);
+}
+
+// One iteration of a strip with the peer transport, on TWO streams.  The two edge tile columns of each fused kernel —
+// the only tiles that read ghost columns (boundary kernel) or produce the columns the neighbours need (advection
+// kernel) — run on the high-priority communication stream BESIDE the interior tile columns on the compute stream,
+// together with the wait for the neighbours' columns and the push of this rank's:
+//
+//   compute stream   [wait advE(i-1)]  pvb interior          [wait pvbE]  adv interior
+//   comm stream      [wait advI(i-1)]  wait ghosts(i-1), pvb edges  [wait pvbI]  adv edges, handshake, push(i)
+//
+// Edge launches are 2 of ~130 (2 GPUs) .. 33 (8 GPUs) tile columns; as launches of their own on the compute stream each
+// costs a drain + refill of the whole GPU (measured +0.05 / +0.08 ms per iteration at 2 GPUs, profiles/r3_multi_gpu.md).
+// Cross dependencies: the interior tile column next to an edge stages 4 of the edge's columns, and vice versa.
+int fused_iteration_overlapped(wsb_sim* s) {
+  set_iter_uniform(s);
+  const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;
+  cudaStream_t cs = s->comm_stream;
+  CK(cudaStreamWaitEvent(s->stream, s->evEdge, 0));  // advection edges of the previous iteration
+  {
+    ProfScope prof(s, WSB_KERNEL_PVB);
+    if (launch_pvb(s, s->stream, kTX, s->pvbInnerEnd, kNoGap, 0)) return 1;
+  }
+  CK(cudaEventRecord(s->evPvbI, s->stream));
+  CK(cudaStreamWaitEvent(cs, s->evAdvI, 0));         // advection interior of the previous iteration
+  if (s->exch_pending) {
+    if (wait_ghosts(s, cs)) return 1;
+    s->exch_pending = false;
+  }
+  {
+    ProfScope prof(s, WSB_KERNEL_EDGE, cs);
+    if (launch_pvb(s, cs, 0, s->pitch, kTX, s->pvbInnerEnd - kTX)) return 1;
+  }
+  CK(cudaEventRecord(s->evPvbE, cs));
+  s->fb_dirty = false;
+  CK(cudaStreamWaitEvent(s->stream, s->evPvbE, 0));
+  {
+    ProfScope prof(s, WSB_KERNEL_ADV);
+    if (launch_adv(s, s->stream, src, dst, kTX, s->advEdgeStart, kNoGap, 0)) return 1;
+  }
+  CK(cudaEventRecord(s->evAdvI, s->stream));
+  CK(cudaStreamWaitEvent(cs, s->evPvbI, 0));
+  {
+    ProfScope prof(s, WSB_KERNEL_EDGE, cs);
+    if (launch_adv(s, cs, src, dst, 0, s->pitch, kTX, s->advEdgeStart - kTX)) return 1;
+  }
+  CK(cudaEventRecord(s->evEdge, cs));
+  s->even = !s->even;
+  s->pressure_pending = true;
+  XPlanes xp;
+  strip_exchange_planes(s, dst, xp);
+  if (push_ghosts(s, xp)) return 1;
+  s->iter++;
+  return 0;
+}
+
 int fused_iteration(wsb_sim* s) {
+  if (s->peer_mode && s->pvbInnerEnd > kTX && s->advEdgeStart > kTX) return fused_iteration_overlapped(s);
   set_iter_uniform(s);
   const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;
   const bool particles = s->dp.p.enablePrecipitation && s->ND > 0;
-  const int tilesY = (s->H + kTY - 1) / kTY;
-  constexpr int kNoGap = 0x7fffffff;
   // pressure(previous iteration) -> velocity -> curl -> vorticity -> boundary; also clears the
   // feedback / deposition cells it has consumed (app.js:5933-5934 folded in)
   {
     ProfScope prof(s, WSB_KERNEL_PVB);
-    GlobalCtx c = make_ctx(s, 1, 1, 1, 0);
-    TileMaps<11> maps;
-    for (int k = 0; k < 4; k++) {
-      maps.m[k] = s->base[1].map3[k];
-      maps.m[5 + k] = s->water[1].map0[k];
-    }
-    maps.m[4] = s->wallMap3[1];
-    maps.m[9] = s->light[0].map0[0];   // SUNLIGHT
-    maps.m[10] = s->light[0].map0[1];  // NET_HEATING
-    // tile columns [cx0, cx1) minus [gapAt, gapAt + gapLen)
-    auto launch_pvb = [&](int cx0, int cx1, int gapAt, int gapLen) {
-      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
-      k_fused_pvb<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, tilesY), kNT, kSmem1, s->stream>>>(
-          c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
-          s->base[0].p, s->water[0].p, s->wall[0]);
-      return check_launch(s, "k_fused_pvb");
-    };
-    // While the previous iteration's ghost exchange is still in flight, run the tiles whose staged
-    // region (tile + 4 columns) stays clear of the ghost columns; then wait for the neighbours'
-    // columns; then the two edge tile columns (one launch).
+    // NCCL transport: while the previous iteration's ghost exchange is still in flight, run the tiles whose staged
+    // region (tile + 4 columns) stays clear of the ghost columns; then wait for the neighbours' columns; then the two
+    // edge tile columns (one launch).
     const int innerEnd = s->pvbInnerEnd;
     if (s->exch_pending && innerEnd > kTX) {
-      if (launch_pvb(kTX, innerEnd, kNoGap, 0)) return 1;
+      if (launch_pvb(s, s->stream, kTX, innerEnd, kNoGap, 0)) return 1;
       if (join_exchange(s)) return 1;
-      if (launch_pvb(0, s->pitch, kTX, innerEnd - kTX)) return 1;
+      if (launch_pvb(s, s->stream, 0, s->pitch, kTX, innerEnd - kTX)) return 1;
     } else {
       if (join_exchange(s)) return 1;
-      if (launch_pvb(0, s->pitch, kNoGap, 0)) return 1;
+      if (launch_pvb(s, s->stream, 0, s->pitch, kNoGap, 0)) return 1;
     }
   }
   s->fb_dirty = false;
-  // advection (+ condensation ...) -> lighting.  On a strip with the peer transport the two edge tile
-  // columns (which produce the columns the neighbours need) go first, so that the push of the ghost
-  // columns runs beside the interior tiles.
-  const bool edgeFirst = s->peer_mode && s->advEdgeStart > kTX;
+  // advection (+ condensation ...) -> lighting
   {
     ProfScope prof(s, WSB_KERNEL_ADV);
-    TileMaps<12> maps;
-    for (int k = 0; k < 4; k++) {
-      maps.m[k] = s->base[0].map2[k];
-      maps.m[4 + k] = s->water[0].map2[k];
-    }
-    maps.m[8] = s->wallMap2[0];
-    maps.m[9] = s->light[src].map2[0];   // SUNLIGHT
-    maps.m[10] = s->light[src].map2[2];  // IR_DOWN
-    maps.m[11] = s->light[src].map2[3];  // IR_UP
-    GlobalCtx c = make_ctx(s, 0, 0, 0, src);
-    auto launch_adv = [&](int cx0, int cx1, int gapAt, int gapLen) {
-      c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
-      k_fused_adv<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, tilesY), kNT, kSmem2, s->stream>>>(
-          c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->sndT, s->sndW, s->sndV, s->base[1].p, s->water[1].p, s->wall[1],
-          s->light[dst].p, s->maxv);
-      return check_launch(s, "k_fused_adv");
-    };
     if (join_push(s)) return 1;  // the previous push has finished reading the columns this kernel overwrites
-    if (edgeFirst) {
-      if (launch_adv(0, s->pitch, kTX, s->advEdgeStart - kTX)) return 1;
-      CK(cudaEventRecord(s->evEdge, s->stream));
-      if (launch_adv(kTX, s->advEdgeStart, kNoGap, 0)) return 1;
-    } else {
-      if (launch_adv(0, s->pitch, kNoGap, 0)) return 1;
-    }
+    if (launch_adv(s, s->stream, src, dst, 0, s->pitch, kNoGap, 0)) return 1;
   }
   s->even = !s->even;
   s->pressure_pending = true;
   if (particles && precipitation(s)) return 1;
   if (s->cfg.n_ranks > 1) {
     XPlanes xp;
-    add_planes(xp, s->base[1]);
-    add_planes(xp, s->water[1]);
-    add_wall(xp, s, 1);
-    add_planes(xp, s->light[dst]);
-    if (exchange(s, xp, edgeFirst)) return 1;
+    strip_exchange_planes(s, dst, xp);
+    if (exchange(s, xp)) return 1;
   }
   s->iter++;
   return 0;
@@ -693,7 +746,7 @@ int dry_iteration(wsb_sim* s) {
     if (s->cfg.n_ranks > 1) {
       XPlanes xp;
       add_planes(xp, s->base[1]);
-      if (exchange(s, xp, false) || join_exchange(s) || join_push(s)) return 1;
+      if (exchange(s, xp) || join_exchange(s) || join_push(s)) return 1;
     }
   }
   s->iter++;
@@ -993,7 +1046,10 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
           (e = cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s->evExch, cudaEventDisableTiming)) != cudaSuccess ||
           (e = cudaEventCreateWithFlags(&s->evEdge, cudaEventDisableTiming)) != cudaSuccess ||
-          (e = cudaEventCreateWithFlags(&s->evPush, cudaEventDisableTiming)) != cudaSuccess) {
+          (e = cudaEventCreateWithFlags(&s->evPush, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evPvbI, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evPvbE, cudaEventDisableTiming)) != cudaSuccess ||
+          (e = cudaEventCreateWithFlags(&s->evAdvI, cudaEventDisableTiming)) != cudaSuccess) {
         rc = fail("wsb_create: %s", cudaGetErrorString(e));
         break;
       }
@@ -1040,6 +1096,9 @@ int wsb_destroy(wsb_sim* s) {
   cudaFree(s->arena);
   if (s->evEdge) cudaEventDestroy(s->evEdge);
   if (s->evPush) cudaEventDestroy(s->evPush);
+  if (s->evPvbI) cudaEventDestroy(s->evPvbI);
+  if (s->evPvbE) cudaEventDestroy(s->evPvbE);
+  if (s->evAdvI) cudaEventDestroy(s->evAdvI);
   cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
   cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
   cudaFree(s->lightning); cudaFree(s->inactive); cudaFree(s->maxv); cudaFree(s->scratch);
@@ -1415,7 +1474,7 @@ int wsb_set_profiling(wsb_sim* s, int32_t on) {
 
 int wsb_kernel_time_ms(wsb_sim* s, int32_t kernel, float* total_ms, int32_t* launches) {
   if (!s || !total_ms || !launches) return fail("wsb_kernel_time_ms: null argument");
-  if (kernel < 0 || kernel > WSB_KERNEL_WAIT) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
+  if (kernel < 0 || kernel > WSB_KERNEL_EDGE) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
   if (use_device(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
   double sum = 0.0;

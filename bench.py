@@ -326,7 +326,7 @@ def run_ours(args):
     clocks = sampler.result()
     launches = sim.launch_count - launches0
     kt = {name: sim.kernel_time_ms(k) for name, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("halo", S.KERNEL_HALO),
-                                                       ("ghost_wait", S.KERNEL_WAIT))}
+                                                       ("ghost_wait", S.KERNEL_WAIT), ("edge_tiles", S.KERNEL_EDGE))}
     ms_mine = ms
     ms = _max_over_ranks(ms, world, device)
     value = W * H * K / (ms * 1e-3)

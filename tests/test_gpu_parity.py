@@ -97,6 +97,70 @@ def test_per_pass_parity(case, save100):
 
 
 # ---------------------------------------------------------------------------------------------
+# the reference's own output: every shipped save that is available (all 14 with the reference checkout, the committed
+# 100 x 100 save and two 512-column crops otherwise; tests/test_reference_saves.py holds the oracle to the same files)
+# ---------------------------------------------------------------------------------------------
+from test_reference_saves import SAVES, check_wall_pins  # noqa: E402
+
+
+@pytest.mark.parametrize("name,path,margin", SAVES, ids=[s_[0] for s_ in SAVES])
+def test_per_pass_parity_on_reference_saves(name, path, margin):
+    """One whole iteration pass by pass (REFERENCE schedule) on the reference's own state, every buffer after every pass
+    against the oracle: bit-exact; droplets bit-exact, sprite sums up to summation order."""
+    sf = wsb200.savefile.load(path)
+    g = P.resolve_settings(sf.settings_json)
+    sim = make_cuda(g, sf.base, sf.water, sf.wall, sf.droplets, SIM.SCHEDULE_REFERENCE)
+    ora = make_oracle(g, sf.base, sf.water, sf.wall, sf.droplets)
+    sim.iter_num = 100   # a multiple of 100: the slow surface processes (snow / soil smoothing, growth ticks) take part
+    ora.iter = 100
+    for pname, pid in PASSES:
+        sim.run_pass(pid)
+        ora.run_pass(pid)
+        if pid == SIM.PASS_PRECIPITATION:
+            assert np.array_equal(sim.read_droplets(), ora.droplets()), f"{name}: droplets differ"
+            fb_got, fb_want = sim.read_pixels(SIM.FIELD_FEEDBACK), ora.field(O.FIELD_FEEDBACK)
+            assert np.array_equal(fb_got != 0, fb_want != 0)
+            assert np.allclose(fb_got, fb_want, rtol=1e-5, atol=1e-9)
+            assert np.allclose(sim.read_pixels(SIM.FIELD_DEPOSITION), ora.field(O.FIELD_DEPOSITION), rtol=1e-5, atol=1e-9)
+            break
+        for fname, got, want in _all_buffers(sim, ora):
+            same = (got == want) | ((got != got) & (want != want))
+            assert same.all(), f"{name}, pass {pname}: {fname} differs in {np.count_nonzero(~same)} values"
+    sim.close()
+
+
+@pytest.mark.parametrize("name,path,margin", SAVES, ids=[s_[0] for s_ in SAVES])
+def test_fused_iteration_keeps_reference_saves_fixed(name, path, margin):
+    """The product path on the reference's own output: one fused iteration leaves TYPE / DISTANCE / VERT_DISTANCE and the
+    land-surface vegetation of the save unchanged (the pins of tests/test_reference_saves.py, here on the GPU), and two
+    iterations agree with the oracle: wall bit-exact, fp32 fields within the north-star tolerance (the particle pass
+    has fed back once, with sprite sums in a different order)."""
+    sf = wsb200.savefile.load(path)
+    g = P.resolve_settings(sf.settings_json)
+    sim = make_cuda(g, sf.base, sf.water, sf.wall, sf.droplets, SIM.SCHEDULE_FUSED)
+    ora = make_oracle(g, sf.base, sf.water, sf.wall, sf.droplets)
+    sim.iter_num = 7
+    ora.iter = 7
+    sim.step(1)
+    ora.step(1)
+    wall1 = sim.read_pixels(SIM.FIELD_WALL)
+    check_wall_pins(sf, wall1, margin, name)
+    assert np.array_equal(wall1, ora.field(O.FIELD_WALL, 0))
+    assert np.array_equal(sim.read_pixels(SIM.FIELD_BASE), ora.field(O.FIELD_BASE, 0)), f"{name}: base after one fused iteration"
+    sim.step(1)
+    ora.step(1)
+    assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), ora.field(O.FIELD_WALL, 0))
+    for fname, got, want in (("base", sim.read_pixels(SIM.FIELD_BASE), ora.field(O.FIELD_BASE, 0)),
+                             ("water", sim.read_pixels(SIM.FIELD_WATER, view=1), ora.field(O.FIELD_WATER, 1)),
+                             ("light", sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_LATEST), ora.light_latest())):
+        # overlapping sprites add up to thousands of signed contributions per texel (growth against evaporation): the
+        # two summation orders differ by rounding relative to the LARGEST term, not to the (cancelled) sum — hence the
+        # absolute term: 1e-6 g/kg resp. K on fields of order 1 .. 300 (measured worst case 5e-8, 'Awesome Convergence Cell')
+        assert np.allclose(got, want, rtol=REL, atol=1e-6), f"{name}: {fname} after two fused iterations: rel err {rel_err(got, want):.3g}, max abs {np.abs(got - want).max():.3g}"
+    sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
 # whole iterations
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
@@ -121,6 +185,40 @@ def test_golden_vectors_100x100(schedule, save100):
         assert np.allclose(d_got, d_want, rtol=1e-4, atol=1e-6)
     assert sim.iter_num == 100
     sim.close()
+
+
+def test_drift_curve_1_10_100_1000(save100):
+    """BASELINE config 1 (saves/100 X 100 Test, 1000 iterations) on the fused path against the oracle: the drift curve
+    SURVEY 4 asks for.  Without particles the two are bit-identical for all 1000 iterations; with the particle pass the
+    sprite sums differ in summation order (float atomics), which the weather amplifies slowly: the curve is written to
+    gpurun_out/drift_curve.json and bounded by the north-star tolerance."""
+    import json
+
+    curve = {}
+    for particles in (False, True):
+        g = P.resolve_settings(save100.settings_json)
+        g["enablePrecipitation"] = particles
+        drops = save100.droplets if particles else None
+        sim = make_cuda(g, save100.base, save100.water, save100.wall, drops, SIM.SCHEDULE_FUSED)
+        ora = make_oracle(g, save100.base, save100.water, save100.wall, drops)
+        done = 0
+        for n in (1, 10, 100, 1000):
+            sim.step(n - done)
+            ora.step(n - done)
+            done = n
+            assert np.array_equal(sim.read_pixels(SIM.FIELD_WALL), ora.field(O.FIELD_WALL, 0)), f"wall after {n} iterations (particles={particles})"
+            errs = {"base": rel_err(sim.read_pixels(SIM.FIELD_BASE), ora.field(O.FIELD_BASE, 0)),
+                    "water": rel_err(sim.read_pixels(SIM.FIELD_WATER, view=1), ora.field(O.FIELD_WATER, 1)),
+                    "light": rel_err(sim.read_pixels(SIM.FIELD_LIGHT, view=SIM.VIEW_LATEST), ora.light_latest())}
+            curve[f"particles={particles},n={n}"] = errs
+            if not particles:
+                assert max(errs.values()) == 0.0, f"no particles, {n} iterations: {errs}"
+            else:
+                assert max(errs.values()) < REL, f"with particles, {n} iterations: {errs}"
+        sim.close()
+    os.makedirs(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "drift_curve.json"), "w") as f:
+        json.dump(curve, f, indent=1)
 
 
 @pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
@@ -192,6 +290,60 @@ def test_inactive_latch_and_lightning():
     # iterNum 0 is a multiple of 600: the latch fires in the first iteration
     assert sim.inactive_droplets == ora.inactive_droplets > 0
     assert np.array_equal(sim.lightning, ora.lightning)
+    sim.close()
+
+
+def _thunderstorm(seed, cold_cloud, w=64, h=48):
+    """Dense sub-zero cloud aloft and a pool of inactive droplets: snow spawns at once and, with the last bolt more than
+    30 iterations ago, some spawn turns into a lightning bolt (precipitationShader.vert:121-140)."""
+    g, base, water, wall, _ = stress_state(w, h, seed=seed)
+    g["enablePrecipitation"] = True
+    rng = np.random.default_rng(seed)
+    air = wall[..., 1] != 0
+    f32 = np.float32
+    water[h // 2:, :, 1] += np.where(air[h // 2:], f32(cold_cloud), f32(0.0))
+    water[h // 2:, :, 0] += np.where(air[h // 2:], f32(cold_cloud), f32(0.0))
+    n = 400
+    drops = np.zeros((n, 5), f32)
+    drops[:, 0] = rng.uniform(-1, 1, n)
+    drops[:, 1] = rng.uniform(-0.95, 0.95, n)
+    drops[:, 2] = -2.0 - rng.uniform(-1, 1, n)
+    drops[:, 4] = 1.0
+    return g, base, water, wall, drops
+
+
+@pytest.mark.parametrize("schedule", [SIM.SCHEDULE_REFERENCE, SIM.SCHEDULE_FUSED])
+@pytest.mark.parametrize("seed,cold_cloud,first", [(21, 5.0, 1), (22, 5.0, 1), (20, 7.0, 2), (23, 7.0, 3)])
+def test_lightning_bolt_strikes_and_is_latched(schedule, seed, cold_cloud, first):
+    """A bolt on the GPU: the spawn branch of precipitationShader.vert:121-140 (1-pixel sprite into feedback pixel
+    (1, 0)) and the latch of lightningLocationShader.frag:24-38, against the oracle.  `first` = the iteration the
+    oracle's bolt strikes in; until then no particle has fed back into the fluid, so the record is bit-exact."""
+    g, base, water, wall, drops = _thunderstorm(seed, cold_cloud)
+    p = P.derive_params(g)
+    p.spawnChanceMult = 0.02
+    sim = make_cuda(g, base, water, wall, drops, schedule)
+    ora = make_oracle(g, base, water, wall, drops)
+    sim.set_params(p)
+    ora.set_params(p)
+    sim.iter_num = 77
+    ora.iter = 77
+    bolt_iter = None
+    for it in range(1, first + 2):
+        sim.step(1)
+        ora.step(1)
+        got, want = sim.lightning, ora.lightning
+        if it < first:
+            assert not want.any() and not got.any(), f"iteration {it}: unexpected bolt {got} / {want}"
+        elif it == first:
+            assert want[2] > 76.0 and want[3] > 0.0, f"the oracle's bolt did not strike in iteration {first}: {want}"
+            if first == 1:
+                assert np.array_equal(got, want), f"bolt record {got} vs {want}"
+            else:
+                assert np.allclose(got, want, rtol=1e-5, atol=0), f"bolt record {got} vs {want}"
+            bolt_iter = got[2]
+        else:  # 30 iterations must pass before the next bolt: the record is kept (discard branch of the latch)
+            assert np.allclose(got, want, rtol=1e-5, atol=0) and got[2] == bolt_iter
+    assert np.array_equal(sim.read_droplets()[:, 2] < 0, ora.droplets()[:, 2] < 0)  # the striking droplet went inactive in both
     sim.close()
 
 

@@ -37,7 +37,7 @@ from oracle import oracle as O
 
 P = wsb200.params
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-REFERENCE_SAVES = "/root/reference/saves"
+REFERENCE_SAVES = os.environ.get("WSB_REFERENCE_SAVES", "/root/reference/saves")  # the GPU box has no reference checkout
 SEAM_MARGIN = 136  # crops: DISTANCE saturates at 127, so the seam cannot reach further
 TYPE, DISTANCE, VERT_DISTANCE, VEGETATION = range(4)
 LAND, WATER, FIRE = 1, 2, 3
