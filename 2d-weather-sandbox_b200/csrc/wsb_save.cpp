@@ -132,4 +132,73 @@ int64_t wsb_save_decompress(const uint8_t* z, int64_t zn, uint8_t* out, int64_t 
 
 int64_t wsb_save_inflated_size(const uint8_t* z, int64_t zn) { return inflate_impl(z, zn, nullptr, 0, true); }
 
+// --- container (loadData app.js:1256-1366, prepareDownload app.js:6575-6628) ---------------------------------
+int32_t wsb_save_parse(const uint8_t* payload, int64_t n, uint32_t version, wsb_save_layout* out) {
+  if (!payload || !out || n < 0) return -1;
+  if (version != WSB_SAVE_VERSION_ID && version != WSB_SAVE_LEGACY_VERSION_ID) return -4;
+  if (n < 4) return -5;
+  wsb_save_layout L;
+  memset(&L, 0, sizeof L);
+  L.width = payload[0] | (payload[1] << 8);   // Uint16Array(buffer.slice(0, 4)), little endian
+  L.height = payload[2] | (payload[3] << 8);
+  const int64_t cells = (int64_t)L.width * L.height;
+  L.n_droplets = cells / 25;
+  L.off_base = 4;
+  L.off_water = L.off_base + cells * 16;
+  L.off_wall = L.off_water + cells * 16;
+  L.off_droplets = L.off_wall + cells * 4;
+  int64_t off = L.off_droplets + L.n_droplets * 20;
+  if (n < off) return -5;
+  L.off_settings = -1;
+  if (version == WSB_SAVE_VERSION_ID) {
+    if (n < off + 2) return -5;
+    L.n_stations = (int16_t)(payload[off] | (payload[off + 1] << 8));
+    if (L.n_stations < 0) return -5;
+    L.off_stations = off + 2;
+    off = L.off_stations + L.n_stations * 4;
+    if (n < off) return -5;
+    L.off_settings = off;
+    L.settings_len = n - off;
+  }
+  *out = L;
+  return 0;
+}
+
+int64_t wsb_save_payload_size(int32_t width, int32_t height, int32_t n_stations, int64_t settings_len, uint32_t version) {
+  if (width <= 0 || height <= 0 || width > 65535 || height > 65535 || n_stations < 0 || settings_len < 0) return -1;
+  if (version != WSB_SAVE_VERSION_ID && version != WSB_SAVE_LEGACY_VERSION_ID) return -4;
+  const int64_t cells = (int64_t)width * height;
+  int64_t n = 4 + cells * 36 + (cells / 25) * 20;
+  if (version == WSB_SAVE_VERSION_ID) n += 2 + (int64_t)n_stations * 4 + settings_len;
+  return n;
+}
+
+int64_t wsb_save_serialise(uint8_t* out, int64_t out_cap, int32_t width, int32_t height, const float* base, const float* water,
+                           const int8_t* wall, const float* droplets, const int16_t* stations, int32_t n_stations,
+                           const char* settings, int64_t settings_len, uint32_t version) {
+  const int64_t need = wsb_save_payload_size(width, height, n_stations, settings_len, version);
+  if (need < 0) return need;
+  if (!out || !base || !water || !wall) return -1;
+  if (out_cap < need) return -2;
+  const int64_t cells = (int64_t)width * height, nd = cells / 25;
+  if (nd > 0 && !droplets) return -1;
+  uint8_t* p = out;
+  p[0] = (uint8_t)(width & 0xff); p[1] = (uint8_t)(width >> 8); p[2] = (uint8_t)(height & 0xff); p[3] = (uint8_t)(height >> 8);
+  p += 4;
+  memcpy(p, base, (size_t)cells * 16); p += cells * 16;     // x86 / aarch64 hosts are little endian, like the typed arrays of the reference
+  memcpy(p, water, (size_t)cells * 16); p += cells * 16;
+  memcpy(p, wall, (size_t)cells * 4); p += cells * 4;
+  if (nd) memcpy(p, droplets, (size_t)nd * 20);
+  p += nd * 20;
+  if (version == WSB_SAVE_VERSION_ID) {
+    p[0] = (uint8_t)(n_stations & 0xff); p[1] = (uint8_t)((n_stations >> 8) & 0xff);   // Uint16Array.of(weatherStations.length)
+    p += 2;
+    if (n_stations) { if (!stations) return -1; memcpy(p, stations, (size_t)n_stations * 4); }
+    p += (int64_t)n_stations * 4;
+    if (settings_len) { if (!settings) return -1; memcpy(p, settings, (size_t)settings_len); }
+    p += settings_len;
+  }
+  return p - out;
+}
+
 }  // extern "C"

@@ -28,6 +28,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CODEC = None
 
 
+class SaveLayout(ctypes.Structure):
+    """wsb_save_layout (include/wsb_save.h): byte offsets of the pieces of an inflated payload."""
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32)] + [
+        (n, ctypes.c_int64) for n in ("n_droplets", "off_base", "off_water", "off_wall", "off_droplets", "n_stations", "off_stations",
+                                      "off_settings", "settings_len")]
+
+
 def native_codec():
     """libwsbsave.so (csrc/wsb_save.cpp): multi-threaded zlib codec, or None when it is not built
     (the pure-Python zlib path below produces the same container, on one thread)."""
@@ -47,6 +54,13 @@ def native_codec():
             L.wsb_save_decompress.argtypes = [vp, i64, vp, i64]
             L.wsb_save_inflated_size.restype = i64
             L.wsb_save_inflated_size.argtypes = [vp, i64]
+            L.wsb_save_parse.restype = ctypes.c_int32
+            L.wsb_save_parse.argtypes = [vp, i64, ctypes.c_uint32, ctypes.POINTER(SaveLayout)]
+            L.wsb_save_payload_size.restype = i64
+            L.wsb_save_payload_size.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, i64, ctypes.c_uint32]
+            L.wsb_save_serialise.restype = i64
+            L.wsb_save_serialise.argtypes = [vp, i64, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.c_int32, ctypes.c_char_p, i64,
+                                             ctypes.c_uint32]
             _CODEC = L
     return _CODEC or None
 
@@ -118,6 +132,9 @@ def loads(blob: bytes) -> SaveFile:
         data = inflate(blob[4:])
     except zlib.error as e:
         raise IncompatibleFile(f"payload is not a zlib stream: {e}")
+    L = native_codec()
+    if L is not None:  # the C++ reader (csrc/wsb_save.cpp: wsb_save_parse); the Python below is its fallback and cross-check
+        return _loads_native(L, data, version)
     w, h = struct.unpack_from("<HH", data, 0)
     n = w * h
     nd = num_droplets(w, h)
@@ -144,15 +161,51 @@ def loads(blob: bytes) -> SaveFile:
     return SaveFile(w, h, base, water, wall, drops, stations, settings, version)
 
 
+def _loads_native(L, data: bytes, version: int) -> SaveFile:
+    lay = SaveLayout()
+    buf = np.frombuffer(data, np.uint8)
+    rc = L.wsb_save_parse(buf.ctypes.data, buf.size, version, ctypes.byref(lay))
+    if rc != 0:
+        raise IncompatibleFile({-4: f"unknown save file version id {version}", -5: f"payload truncated ({len(data)} bytes)"}.get(rc, f"wsb_save_parse failed ({rc})"))
+    w, h, n = lay.width, lay.height, lay.width * lay.height
+    base = np.frombuffer(data, "<f4", n * 4, lay.off_base).reshape(h, w, 4).copy()
+    water = np.frombuffer(data, "<f4", n * 4, lay.off_water).reshape(h, w, 4).copy()
+    wall = np.frombuffer(data, "i1", n * 4, lay.off_wall).reshape(h, w, 4).copy()
+    drops = np.frombuffer(data, "<f4", lay.n_droplets * 5, lay.off_droplets).reshape(lay.n_droplets, 5).copy()
+    stations, settings = np.zeros((0, 2), np.int16), None
+    if lay.off_settings >= 0:
+        stations = np.frombuffer(data, "<i2", lay.n_stations * 2, lay.off_stations).reshape(lay.n_stations, 2).copy()
+        settings = data[lay.off_settings:lay.off_settings + lay.settings_len].decode("utf-8")
+    return SaveFile(w, h, base, water, wall, drops, stations, settings, version)
+
+
 def load(path: str) -> SaveFile:
     with open(path, "rb") as f:
         return loads(f.read())
 
 
-def payload(sf: SaveFile) -> bytes:
-    """The uncompressed byte stream prepareDownload assembles (app.js:6610-6614)."""
+def payload(sf: SaveFile, native: bool | None = None) -> bytes:
+    """The uncompressed byte stream prepareDownload assembles (app.js:6610-6614); through the C++ writer
+    (wsb_save_serialise) when libwsbsave.so is built (native=False forces the Python restatement)."""
     h, w = sf.height, sf.width
     assert sf.base.shape == (h, w, 4) and sf.water.shape == (h, w, 4) and sf.wall.shape == (h, w, 4)
+    L = native_codec() if native in (None, True) else None
+    if L is not None:
+        st = np.ascontiguousarray(sf.stations, "<i2").reshape(-1, 2)
+        js = (sf.settings_json or "{}").encode("utf-8")
+        cur = sf.version == SAVE_FILE_VERSION_ID
+        size = L.wsb_save_payload_size(w, h, st.shape[0] if cur else 0, len(js) if cur else 0, sf.version)
+        if size < 0:
+            raise ValueError(f"wsb_save_payload_size failed ({size})")
+        out = np.empty(size, np.uint8)
+        arrs = [np.ascontiguousarray(sf.base, "<f4"), np.ascontiguousarray(sf.water, "<f4"), np.ascontiguousarray(sf.wall, "i1"),
+                np.ascontiguousarray(sf.droplets, "<f4")]
+        assert arrs[3].shape == (num_droplets(w, h), 5), "droplet buffer must hold W*H/25 records"
+        m = L.wsb_save_serialise(out.ctypes.data, size, w, h, *[a.ctypes.data for a in arrs], st.ctypes.data if st.size else None, st.shape[0],
+                                 js, len(js), sf.version)
+        if m != size:
+            raise ValueError(f"wsb_save_serialise failed ({m})")
+        return out.tobytes()
     parts = [
         struct.pack("<HH", w, h),
         np.ascontiguousarray(sf.base, "<f4").tobytes(),

@@ -33,6 +33,36 @@ int64_t wsb_save_decompress(const uint8_t* z, int64_t zn, uint8_t* out, int64_t 
 /* Payload length of a zlib stream (inflates into a scratch window; no output buffer needed). */
 int64_t wsb_save_inflated_size(const uint8_t* z, int64_t zn);
 
+/* --- the container itself (loadData app.js:1256-1366, prepareDownload app.js:6575-6628) ---------------------- */
+
+#define WSB_SAVE_VERSION_ID 263574036u         /* app.js:345 */
+#define WSB_SAVE_LEGACY_VERSION_ID 1939327491u /* app.js:1265: no stations, no settings */
+
+/* Where the pieces of an INFLATED payload are (byte offsets into it). */
+typedef struct wsb_save_layout {
+  int32_t width, height;
+  int64_t n_droplets;    /* W*H/25 (NUM_DROPLETS_DEVIDER, app.js:452,1282) */
+  int64_t off_base;      /* f32[H][W][4] */
+  int64_t off_water;     /* f32[H][W][4] */
+  int64_t off_wall;      /* i8 [H][W][4] */
+  int64_t off_droplets;  /* f32[N][5] */
+  int64_t n_stations;    /* 0 for the legacy version */
+  int64_t off_stations;  /* i16[n][2] */
+  int64_t off_settings;  /* UTF-8 JSON of guiControls up to the end of the payload; -1 for the legacy version */
+  int64_t settings_len;
+} wsb_save_layout;
+
+/* loadData: validate and locate.  Returns 0, or -1 bad argument, -4 unknown version id, -5 truncated payload
+ * ('Incompatible file!', app.js:1349). */
+int32_t wsb_save_parse(const uint8_t* payload, int64_t n, uint32_t version, wsb_save_layout* out);
+
+/* prepareDownload: payload size, and assembly into `out` (returns the size written, or negative: -1 bad
+ * argument, -2 out_cap too small, -4 unknown version).  stations / settings are ignored for the legacy version. */
+int64_t wsb_save_payload_size(int32_t width, int32_t height, int32_t n_stations, int64_t settings_len, uint32_t version);
+int64_t wsb_save_serialise(uint8_t* out, int64_t out_cap, int32_t width, int32_t height, const float* base, const float* water,
+                           const int8_t* wall, const float* droplets, const int16_t* stations, int32_t n_stations,
+                           const char* settings, int64_t settings_len, uint32_t version);
+
 #ifdef __cplusplus
 }
 #endif

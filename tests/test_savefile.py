@@ -88,3 +88,38 @@ def test_native_codec_is_a_standard_zlib_stream(built_library):
     t0 = time.perf_counter(); a = S.deflate(big, 6, 1); t1 = time.perf_counter(); b = S.deflate(big, 6, 4); t2 = time.perf_counter()
     assert zlib.decompress(a) == big and zlib.decompress(b) == big
     assert (t2 - t1) < (t1 - t0)
+
+
+# ---------------------------------------------------------------------------------------------
+# every save the reference ships (when the checkout is present), plus the committed fixtures: the C++ reader / writer
+# (csrc/wsb_save.cpp) against the Python restatement and against the file's own bytes
+# ---------------------------------------------------------------------------------------------
+from test_reference_saves import SAVES  # noqa: E402
+
+
+@pytest.mark.parametrize("name,path", [(s_[0], s_[1]) for s_ in SAVES], ids=[s_[0] for s_ in SAVES])
+def test_native_container_round_trips_every_save(name, path, built_library):
+    assert S.native_codec() is not None, "libwsbsave.so must be built (make -C 2d-weather-sandbox_b200/csrc)"
+    blob = open(path, "rb").read()
+    original = zlib.decompress(blob[4:])                      # what pako.inflate hands to loadData
+    sf = S.loads(blob)                                         # C++ inflate + wsb_save_parse
+    assert sf.droplets.shape == (sf.width * sf.height // 25, 5)
+    assert S.payload(sf) == original                           # wsb_save_serialise reassembles the reference's bytes
+    assert S.payload(sf, native=False) == original             # ... and so does the Python writer
+    assert zlib.decompress(S.dumps(sf, level=1)[4:]) == original   # multi-threaded deflate -> one standard zlib stream
+    if sf.settings_json is not None:
+        json.loads(sf.settings_json)
+
+
+def test_native_parser_rejects_what_loaddata_rejects(built_library):
+    import ctypes
+
+    L = S.native_codec()
+    lay = S.SaveLayout()
+    good = np.frombuffer(S.payload(S.SaveFile(32, 32, np.zeros((32, 32, 4), np.float32), np.zeros((32, 32, 4), np.float32), np.zeros((32, 32, 4), np.int8),
+                                              np.zeros((S.num_droplets(32, 32), 5), np.float32), settings_json="{}")), np.uint8)
+    assert L.wsb_save_parse(good.ctypes.data, good.size, S.SAVE_FILE_VERSION_ID, ctypes.byref(lay)) == 0
+    assert (lay.width, lay.height, lay.n_droplets, lay.n_stations, lay.settings_len) == (32, 32, 40, 0, 2)
+    assert L.wsb_save_parse(good.ctypes.data, good.size, 42, ctypes.byref(lay)) == -4            # unknown version id
+    assert L.wsb_save_parse(good.ctypes.data, good.size - 10, S.SAVE_FILE_VERSION_ID, ctypes.byref(lay)) == -5   # truncated
+    assert L.wsb_save_parse(good.ctypes.data, 3, S.SAVE_FILE_VERSION_ID, ctypes.byref(lay)) == -5
