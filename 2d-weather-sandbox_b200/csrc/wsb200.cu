@@ -288,6 +288,7 @@ struct wsb_sim {
   bool use_tma = false;
   float4* fb = nullptr;
   float2 *dep = nullptr, *vort = nullptr;
+  SpriteGrid sg{};  // sprite origins + dirty-tile map of the particle pass (single GPU, n_droplets > 0)
   float* curl = nullptr;
   float* drops[2] = {};
   float *initial_T = nullptr, *sndT = nullptr, *sndW = nullptr, *sndV = nullptr;
@@ -552,6 +553,10 @@ int clear_feedback(wsb_sim* s) {
   if (!s->fb_dirty) return 0;
   CK(cudaMemsetAsync(s->fb, 0, cells(s) * sizeof(float4), s->stream));
   CK(cudaMemsetAsync(s->dep, 0, cells(s) * sizeof(float2), s->stream));
+  if (s->sg.dirtyFb) {
+    CK(cudaMemsetAsync(s->sg.dirtyFb, 0, (size_t)s->sg.tilesX * s->sg.tilesY, s->stream));
+    CK(cudaMemsetAsync(s->sg.dirtyDep, 0, (size_t)s->sg.tilesX * s->sg.tilesY, s->stream));
+  }
   s->launches += 2;
   s->fb_dirty = false;
   return 0;
@@ -566,9 +571,15 @@ int precipitation(wsb_sim* s) {
   set_iter_uniform(s);
   ProfScope prof(s, WSB_KERNEL_PRECIP);
   const int threads = 256, blocks = (s->ND + threads - 1) / threads;
-  k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1].p, s->water[1].p, s->fb, s->dep,
+  k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1].p, s->water[1].p, s->fb, s->dep, s->sg,
                                                      s->lightning, s->inactive, s->g, s->dp, s->ND);
   LAUNCHED("k_precipitation");
+  // sprites = 12 x 12 box filter of the origins, on the tiles that were touched
+  const dim3 tiles(s->sg.tilesX, s->sg.tilesY);
+  k_boxsum<<<tiles, 256, kSmemBox, s->stream>>>(s->sg, s->fb, s->dep, s->W, s->H, s->pitch);
+  LAUNCHED("k_boxsum");
+  k_clear_origins<<<tiles, 256, 0, s->stream>>>(s->sg, s->W, s->H);
+  LAUNCHED("k_clear_origins");
   s->fb_dirty = true;
   s->last_drops = dst;
   k_latch<<<1, 32, 0, s->stream>>>(s->fb, s->inactive, s->lightning, s->dp.iterNum, (s->iter % 600 == 0) ? 1 : 0);
@@ -600,8 +611,8 @@ int launch_pvb(wsb_sim* s, cudaStream_t st, int cx0, int cx1, int gapAt, int gap
   maps.m[10] = s->light[0].map0[1];  // NET_HEATING
   c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
   k_fused_pvb<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, st>>>(
-      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, s->fb_dirty ? 1 : 0, s->fb, s->dep,
-      s->base[0].p, s->water[0].p, s->wall[0]);
+      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, (s->fb_dirty && s->sg.dirtyFb) ? 1 : 0, s->fb, s->dep,
+      s->sg, s->base[0].p, s->water[0].p, s->wall[0]);
   return check_launch(s, "k_fused_pvb");
 }
 int launch_adv(wsb_sim* s, cudaStream_t st, int src, int dst, int cx0, int cx1, int gapAt, int gapLen) {
@@ -818,6 +829,17 @@ int alloc_all(wsb_sim* s) {
   }
   CK(cudaMalloc(&s->fb, n * sizeof(float4)));
   CK(cudaMalloc(&s->dep, n * sizeof(float2)));
+  if (s->ND > 0) {  // particles are single-GPU: pitch == W
+    SpriteGrid& sg = s->sg;
+    sg.Po = s->W + 1;
+    sg.tilesX = (s->W + kPTX - 1) / kPTX;
+    sg.tilesY = (s->H + kPTY - 1) / kPTY;
+    const size_t no = (size_t)sg.Po * (s->H + 1), nt = (size_t)sg.tilesX * sg.tilesY;
+    CK(cudaMalloc(&sg.org4, no * sizeof(float4)));
+    CK(cudaMalloc(&sg.org2, no * sizeof(float2)));
+    CK(cudaMalloc(&sg.dirtyFb, nt));
+    CK(cudaMalloc(&sg.dirtyDep, nt));
+  }
   if (s->schedule == WSB_SCHEDULE_REFERENCE) {
     CK(cudaMalloc(&s->curl, n * sizeof(float)));
     CK(cudaMalloc(&s->vort, n * sizeof(float2)));
@@ -862,6 +884,13 @@ int zero_transients(wsb_sim* s) {
     for (int ch = 0; ch < 4; ch++) CK(cudaMemsetAsync(s->light[k].p.c[ch], 0, n * sizeof(float), s->stream));
   CK(cudaMemsetAsync(s->fb, 0, n * sizeof(float4), s->stream));
   CK(cudaMemsetAsync(s->dep, 0, n * sizeof(float2), s->stream));
+  if (s->sg.org4) {
+    const size_t no = (size_t)s->sg.Po * (s->H + 1), nt = (size_t)s->sg.tilesX * s->sg.tilesY;
+    CK(cudaMemsetAsync(s->sg.org4, 0, no * sizeof(float4), s->stream));
+    CK(cudaMemsetAsync(s->sg.org2, 0, no * sizeof(float2), s->stream));
+    CK(cudaMemsetAsync(s->sg.dirtyFb, 0, nt, s->stream));
+    CK(cudaMemsetAsync(s->sg.dirtyDep, 0, nt, s->stream));
+  }
   if (s->curl) CK(cudaMemsetAsync(s->curl, 0, n * sizeof(float), s->stream));
   if (s->vort) CK(cudaMemsetAsync(s->vort, 0, n * sizeof(float2), s->stream));
   CK(cudaMemsetAsync(s->lightning, 0, 16, s->stream));
@@ -1021,7 +1050,8 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
     }
     if ((e = cudaFuncSetAttribute(k_fused_pvb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_fused_adv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem2)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_fused_dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDry)) != cudaSuccess) {
+        (e = cudaFuncSetAttribute(k_fused_dry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDry)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_boxsum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBox)) != cudaSuccess) {
       rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e));
       break;
     }
@@ -1030,7 +1060,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
        // (several strips in one process: deadlock until the bounded wait runs out).
       cudaFuncAttributes fa;
       const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_push_ghosts, (const void*)k_ghosts_free,
-                           (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation,
+                           (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation, (const void*)k_boxsum, (const void*)k_clear_origins,
                            (const void*)k_latch, (const void*)k_texels_to_planes, (const void*)k_planes_to_texels, (const void*)k_pressure_rect,
                            (const void*)k_gather_points};
       for (const void* f : fns)
@@ -1100,6 +1130,7 @@ int wsb_destroy(wsb_sim* s) {
   if (s->evPvbE) cudaEventDestroy(s->evPvbE);
   if (s->evAdvI) cudaEventDestroy(s->evAdvI);
   cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
+  cudaFree(s->sg.org4); cudaFree(s->sg.org2); cudaFree(s->sg.dirtyFb); cudaFree(s->sg.dirtyDep);
   cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
   cudaFree(s->lightning); cudaFree(s->inactive); cudaFree(s->maxv); cudaFree(s->scratch);
   cudaFree(s->sendL); cudaFree(s->sendR); cudaFree(s->recvL); cudaFree(s->recvR);

@@ -48,6 +48,17 @@ constexpr int kRowStep = kNT / kTX;
 // 16-byte aligned (4 floats), and the stencils need 2..3 of them anyway.
 constexpr int kHX = 4;
 
+// Sprite bookkeeping of the particle pass (wsb_particles.cuh), consumed by k_fused_pvb.
+// Origin grids: [H + 1][W + 1] (the sprite of a droplet at the right / top border starts at pixel W - 6 / H - 6).
+struct SpriteGrid {
+  float4* org4;          // feedback origins
+  float2* org2;          // deposition origins
+  unsigned char* dirtyFb;   // [tilesY][tilesX]: a sprite (or a direct 1-pixel add) touched this tile's feedback texels
+  unsigned char* dirtyDep;  // ... deposition texels
+  int Po;                // origin row pitch = W + 1
+  int tilesX, tilesY;
+};
+
 // ---------------------------------------------------------------------------------------------
 // Tile staging
 // ---------------------------------------------------------------------------------------------
@@ -608,7 +619,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
                                                       const __grid_constant__ DevParams d,
                                                       const __grid_constant__ TileMaps<11> maps, int useTma,
                                                       const float* __restrict__ initial_T, int applyPressure, int useFb,
-                                                      float4* fb, float2* dep, Planes4 baseOut, Planes4 waterOut,
+                                                      float4* fb, float2* dep, SpriteGrid sg, Planes4 baseOut, Planes4 waterOut,
                                                       int* __restrict__ wallOut) {
   WSB_DYN_SMEM(smem_raw);
   float* sVX = reinterpret_cast<float*>(smem_raw);
@@ -630,6 +641,9 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
   const bool colOk = x < g.cx1;
+  // feedback / deposition of the last particle pass: only tiles a sprite touched hold anything
+  const int dirtyIdx = blockIdx.y * sg.tilesX + (X0 + kHX) / kTX;
+  const bool tileFb = useFb && sg.dirtyFb[dirtyIdx] != 0, tileDep = useFb && sg.dirtyDep[dirtyIdx] != 0;
 
   if (tile_tma_ok<kSW1, kSH1>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
@@ -718,21 +732,22 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
       const size_t ci = (size_t)y * g.pitch + x;
       PvbAt c{sVX, sVY, sP, sT2, sVFX, sVFY, sWl, (ty + kH1) * SW + tx + kHX, glob, x, y, sOwn, ty * kTX + tx,
               make_float4(0.f, 0.f, 0.f, 0.f), make_float2(0.f, 0.f)};
-      if (useFb) {
-        c.fb0 = fb[ci];
-        c.dep0 = dep[ci];
-      }
+      if (tileFb) c.fb0 = fb[ci];
+      if (tileDep) c.dep0 = dep[ci];
       float4 b, w;
       char4 wl;
       boundary_cell(c, g, d, initial_T, x, y, b, w, wl);
       baseOut.st(ci, b);
       waterOut.st(ci, w);
       wallOut[ci] = as_int(wl);
-      if (useFb) {  // sprites are sparse: only cells that were hit cost a write
-        if (c.fb0.x != 0.0f || c.fb0.y != 0.0f || c.fb0.z != 0.0f || c.fb0.w != 0.0f) fb[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.dep0.x != 0.0f || c.dep0.y != 0.0f) dep[ci] = make_float2(0.f, 0.f);
-      }
+      // the reference's gl.clear (app.js:5933-5934): only texels that were hit cost a write
+      if (tileFb && (c.fb0.x != 0.0f || c.fb0.y != 0.0f || c.fb0.z != 0.0f || c.fb0.w != 0.0f)) fb[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tileDep && (c.dep0.x != 0.0f || c.dep0.y != 0.0f)) dep[ci] = make_float2(0.f, 0.f);
     }
+  }
+  if (tid == 0) {  // consumed (no other CTA of this launch looks at this tile's flags)
+    if (tileFb) sg.dirtyFb[dirtyIdx] = 0;
+    if (tileDep) sg.dirtyDep[dirtyIdx] = 0;
   }
 }
 

@@ -6,9 +6,20 @@
 // Sprite rule (canonical): window centre = (pos+1)/2 * resolution; a pixel is covered
 // when its centre lies in [c - size/2, c + size/2); clipped to the viewport, never wrapped; a point
 // whose centre is outside the clip volume is discarded.  The reference blends sprites in droplet
-// order; here the adds are L2 atomics (vector red.global.add.v4.f32 / v2.f32), so overlapping
-// sprites sum in arbitrary order — equal up to fp32 rounding of the sum.
+// order — 144 blended pixels per active droplet, its author's "HUGE PERFORMANCE BOTTLENECK"
+// (app.js:5936).  Every pixel of a sprite receives the SAME value, so the sum of all 12 x 12 sprites
+// is a 12 x 12 box filter over the grid of sprite ORIGINS:
+//   k_precipitation  updates the droplets and adds each active droplet ONCE (one vector atomic,
+//                    red.global.add.v4.f32, + one v2 for the rare deposition) to its origin cell,
+//                    marking the <= 4 tiles its sprite touches in a dirty map;
+//   k_boxsum         for dirty 64 x 16 tiles only: origins of the tile + 11-cell apron -> shared
+//                    memory, 12-tap row sums, 12-tap column sums, added to feedback / deposition;
+//   k_clear_origins  zeroes the origin cells of dirty tiles;
+// and k_fused_pvb reads (and clears) feedback / deposition in dirty tiles only.  Overlapping
+// sprites therefore sum in an order of their own — equal to the reference's up to fp32 rounding.
+// 1-pixel sprites (spawn marker, lightning bolt, inactive count) are added to the target directly.
 #pragma once
+#include "wsb_fused_kernels.cuh"
 #include "wsb_ref_kernels.cuh"
 
 namespace wsb {
@@ -172,27 +183,22 @@ __device__ DropletResult droplet_update(const float* __restrict__ din, const Pla
   return r;
 }
 
-// One thread per droplet for the update; the sprites are then rasterised WARP-COOPERATIVELY: each
-// lane that has a sprite broadcasts it in turn and all 32 lanes add one pixel each, walking the
-// sprite's rows — a 12-pixel row is 192 contiguous bytes of the feedback texture, so the vector
-// atomics of one instruction fall into a handful of sectors instead of 32 scattered ones.
-// Inactive droplets (the majority) only count themselves: the count is reduced per block and lands
-// on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
+constexpr int kSpriteSize = 12;             // pntSize of precipitationShader.vert:270
+constexpr int kOriginShift = kSpriteSize / 2;  // origin cell = first covered pixel + 6, in [0, W] x [0, H]
+constexpr int kPTX = kTX, kPTY = kTY;       // dirty-map tiles = the tiles of k_fused_pvb
+
+// One thread per droplet.  Inactive droplets (the majority) only count themselves: the count is
+// reduced per block and lands on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
 __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__ dropsIn, float* __restrict__ dropsOut,
                                                        Planes4 baseT, Planes4 waterT,
-                                                       float4* __restrict__ fb, float2* __restrict__ dep,
+                                                       float4* __restrict__ fb, float2* __restrict__ dep, SpriteGrid sg,
                                                        const float* __restrict__ lightning,
                                                        const float* __restrict__ inactiveUniform, Geom g, DevParams d, int ND) {
   __shared__ int sInactive;
   if (threadIdx.x == 0) sInactive = 0;
   __syncthreads();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
   bool countsInactive = false;
-  // this lane's sprite: origin pixel, size (0 = none), payload
-  int xs = 0, ys = 0, sz = 0;
-  float4 sf = make_float4(0.f, 0.f, 0.f, 0.f);
-  float2 sd = make_float2(0.f, 0.f);
   if (n < ND) {
     DropletResult r = droplet_update(dropsIn + (size_t)n * 5, baseT, waterT, g, d, lightning[2], *inactiveUniform);
     float* o = dropsOut + (size_t)n * 5;
@@ -202,34 +208,115 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
     } else if (r.glX >= -1.0f && r.glX <= 1.0f && r.glY >= -1.0f && r.glY <= 1.0f) {
       const float xw = (r.glX + 1.0f) * 0.5f * g.Wf, yw = (r.glY + 1.0f) * 0.5f * g.Hf;
       const float half = r.pointSize * 0.5f;
-      xs = (int)ceilf(xw - half - 0.5f);
-      ys = (int)ceilf(yw - half - 0.5f);
-      sz = (int)r.pointSize;
-      sf = r.feedback;
-      sd = r.deposition;
-    }
-  }
-  unsigned pending = __ballot_sync(0xffffffffu, sz > 0);
-  while (pending) {
-    const int src = __ffs(pending) - 1;
-    pending &= pending - 1;
-    const int bx = __shfl_sync(0xffffffffu, xs, src), by = __shfl_sync(0xffffffffu, ys, src), bs = __shfl_sync(0xffffffffu, sz, src);
-    const float4 f = make_float4(__shfl_sync(0xffffffffu, sf.x, src), __shfl_sync(0xffffffffu, sf.y, src),
-                                 __shfl_sync(0xffffffffu, sf.z, src), __shfl_sync(0xffffffffu, sf.w, src));
-    const float2 dp = make_float2(__shfl_sync(0xffffffffu, sd.x, src), __shfl_sync(0xffffffffu, sd.y, src));
-    const bool hasDep = (dp.x != 0.0f || dp.y != 0.0f);
-    for (int p = lane; p < bs * bs; p += 32) {
-      const int j = by + p / bs, i = bx + p % bs;
-      if (j >= 0 && j < g.H && i >= 0 && i < g.pitch) {
-        const size_t ci = (size_t)j * g.pitch + i;
-        atomicAdd(&fb[ci], f);
-        if (hasDep) atomicAdd(&dep[ci], dp);
+      const int xs = (int)ceilf(xw - half - 0.5f), ys = (int)ceilf(yw - half - 0.5f);  // first covered pixel
+      const bool hasDep = r.deposition.x != 0.0f || r.deposition.y != 0.0f;
+      if ((int)r.pointSize == kSpriteSize) {
+        const size_t oi = (size_t)(ys + kOriginShift) * sg.Po + (xs + kOriginShift);
+        atomicAdd(&sg.org4[oi], r.feedback);
+        if (hasDep) atomicAdd(&sg.org2[oi], r.deposition);
+        // the sprite covers pixels [xs, xs + 12) x [ys, ys + 12), clipped: at most 2 x 2 tiles
+        const int tx0 = max(xs, 0) / kPTX, tx1 = min(xs + kSpriteSize - 1, g.pitch - 1) / kPTX;
+        const int ty0 = max(ys, 0) / kPTY, ty1 = min(ys + kSpriteSize - 1, g.H - 1) / kPTY;
+        for (int ty = ty0; ty <= ty1; ty++)
+          for (int tx = tx0; tx <= tx1; tx++) {
+            sg.dirtyFb[ty * sg.tilesX + tx] = 1;
+            if (hasDep) sg.dirtyDep[ty * sg.tilesX + tx] = 1;
+          }
+      } else if (xs >= 0 && xs < g.pitch && ys >= 0 && ys < g.H) {  // 1-pixel sprite: spawn marker, lightning bolt
+        const size_t ci = (size_t)ys * g.pitch + xs;
+        atomicAdd(&fb[ci], r.feedback);
+        sg.dirtyFb[(ys / kPTY) * sg.tilesX + xs / kPTX] = 1;
+        if (hasDep) {
+          atomicAdd(&dep[ci], r.deposition);
+          sg.dirtyDep[(ys / kPTY) * sg.tilesX + xs / kPTX] = 1;
+        }
       }
     }
   }
   if (countsInactive) atomicAdd(&sInactive, 1);
   __syncthreads();
-  if (threadIdx.x == 0 && sInactive > 0) atomicAdd(&fb[0], make_float4((float)sInactive, 0.0f, 0.0f, 0.0f));
+  if (threadIdx.x == 0 && sInactive > 0) {
+    atomicAdd(&fb[0], make_float4((float)sInactive, 0.0f, 0.0f, 0.0f));
+    sg.dirtyFb[0] = 1;
+  }
+}
+
+// 12 x 12 box filter of the sprite origins of one dirty tile, added to the target texels.
+//   pixel (x, y) is covered by the sprites whose first pixel lies in [x - 11, x] x [y - 11, y], i.e. whose ORIGIN
+//   cell (first pixel + 6) lies in [x - 5, x + 6] x [y - 5, y + 6].
+constexpr int kBoxW = kPTX + kSpriteSize - 1, kBoxH = kPTY + kSpriteSize - 1;  // 75 x 27 origins per tile
+constexpr int kBoxPitch = kBoxW + 1;
+constexpr size_t kSmemBox = (size_t)(kBoxH * kBoxPitch + kBoxH * kPTX) * sizeof(float4);
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ bool vnonzero(float4 a) { return a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f; }
+__device__ __forceinline__ bool vnonzero(float2 a) { return a.x != 0.0f || a.y != 0.0f; }
+__device__ __forceinline__ void vzero(float4& a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void vzero(float2& a) { a = make_float2(0.f, 0.f); }
+
+template <class V>
+__device__ __forceinline__ void boxsum_tile(const V* __restrict__ org, V* __restrict__ target, int Po, int W, int H, int pitch, int X0,
+                                            int Y0, V* sOrg, V* sRow) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kBoxH * kBoxW; i += blockDim.x) {
+    const int r = i / kBoxW, c = i - r * kBoxW;
+    const int oj = Y0 - (kSpriteSize - 1 - kOriginShift) + r, oi = X0 - (kSpriteSize - 1 - kOriginShift) + c;
+    V v;
+    vzero(v);
+    if (oj >= 0 && oj <= H && oi >= 0 && oi <= W) v = org[(size_t)oj * Po + oi];
+    sOrg[r * kBoxPitch + c] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < kBoxH * kPTX; i += blockDim.x) {  // 12-tap row sums
+    const int r = i / kPTX, c = i - r * kPTX;
+    V a = sOrg[r * kBoxPitch + c];
+#pragma unroll
+    for (int k = 1; k < kSpriteSize; k++) a = vadd(a, sOrg[r * kBoxPitch + c + k]);
+    sRow[i] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < kPTY * kPTX; i += blockDim.x) {  // 12-tap column sums
+    const int ty = i / kPTX, tx = i - ty * kPTX;
+    V a = sRow[ty * kPTX + tx];
+#pragma unroll
+    for (int k = 1; k < kSpriteSize; k++) a = vadd(a, sRow[(ty + k) * kPTX + tx]);
+    const int x = X0 + tx, y = Y0 + ty;
+    if (x < W && y < H && vnonzero(a)) {
+      const size_t ci = (size_t)y * pitch + x;
+      target[ci] = vadd(target[ci], a);  // texels hit by 1-pixel sprites already hold their value
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_boxsum(SpriteGrid sg, float4* __restrict__ fb, float2* __restrict__ dep, int W, int H, int pitch) {
+  const int tile = blockIdx.y * sg.tilesX + blockIdx.x;
+  const bool doFb = sg.dirtyFb[tile] != 0, doDep = sg.dirtyDep[tile] != 0;
+  if (!doFb && !doDep) return;
+  WSB_DYN_SMEM(smem_raw);
+  float4* sOrg = reinterpret_cast<float4*>(smem_raw);
+  float4* sRow = sOrg + kBoxH * kBoxPitch;
+  const int X0 = blockIdx.x * kPTX, Y0 = blockIdx.y * kPTY;
+  if (doFb) boxsum_tile<float4>(sg.org4, fb, sg.Po, W, H, pitch, X0, Y0, sOrg, sRow);
+  if (doDep) boxsum_tile<float2>(sg.org2, dep, sg.Po, W, H, pitch, X0, Y0, reinterpret_cast<float2*>(sOrg), reinterpret_cast<float2*>(sRow));
+}
+
+// Every non-zero origin cell lies inside its own sprite, i.e. inside a dirty tile (or in the extra column W / row H,
+// which the last tile column / row owns): zero the origin cells of dirty tiles.  A kernel of its own because the
+// box sums of neighbouring tiles read each other's origins.
+__global__ void __launch_bounds__(256) k_clear_origins(SpriteGrid sg, int W, int H) {
+  const int tile = blockIdx.y * sg.tilesX + blockIdx.x;
+  const bool doFb = sg.dirtyFb[tile] != 0, doDep = sg.dirtyDep[tile] != 0;
+  if (!doFb && !doDep) return;
+  const int X0 = blockIdx.x * kPTX, Y0 = blockIdx.y * kPTY;
+  const int X1 = (blockIdx.x == (unsigned)sg.tilesX - 1) ? W + 1 : X0 + kPTX, Y1 = (blockIdx.y == (unsigned)sg.tilesY - 1) ? H + 1 : Y0 + kPTY;
+  const int w = X1 - X0, n = w * (Y1 - Y0);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / w, c = i - r * w;
+    const size_t oi = (size_t)(Y0 + r) * sg.Po + X0 + c;
+    if (doFb) sg.org4[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (doDep) sg.org2[oi] = make_float2(0.f, 0.f);
+  }
 }
 
 // app.js:5957-5967 (every 600th iteration) + lightningLocationShader.frag:24-38, on device.

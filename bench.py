@@ -315,8 +315,8 @@ def run_ours(args):
         sim.sync()
     sim.step(Wm)
     sim.sync()
-    _barrier(world)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)  # NVML initialisation takes tens of ms, differently on every rank: BEFORE the barrier —
+    _barrier(world)                     # a rank that starts late makes its neighbours wait inside their timed region
     sampler.start()
     launches0 = sim.launch_count
     sim.step(K)
@@ -351,6 +351,7 @@ def run_ours(args):
 
     # ---- sustained: the median of further batches of K steps ---------------------------------
     sus_sampler = ClockSampler(local_rank)
+    _barrier(world)
     sus_sampler.start()
     batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES, world, device)
     sus_clocks = sus_sampler.result()
