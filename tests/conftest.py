@@ -115,6 +115,7 @@ def _load_emu(name="libemufused.so", flags=None):
     L.ef_read_feedback.argtypes = [vp, vp, vp]
     L.ef_get_latches.argtypes = [vp, vp, vp]
     L.ef_set_inactive.argtypes = [vp, ctypes.c_float]
+    L.ef_origin_residue.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
     return L
 
 

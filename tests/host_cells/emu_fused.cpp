@@ -33,6 +33,11 @@ struct Sim {
   std::vector<int> wall[2];
   std::vector<float4> fb;
   std::vector<float2> dep;
+  // sprite origins + dirty-tile map of the particle pass (csrc/wsb200.cu: alloc_all)
+  std::vector<float4> org4;
+  std::vector<float2> org2;
+  std::vector<unsigned char> dirtyFb, dirtyDep;
+  SpriteGrid sg{};
   std::vector<float> initial_T, sndT, sndW, sndV;
   unsigned maxv = 0;
   std::vector<float> drops[2];
@@ -78,11 +83,11 @@ void fused_iteration(Sim& s) {
     maps.m[9] = map_of(s, s.light[0].p.c[0], kTX, kTY);
     maps.m[10] = map_of(s, s.light[0].p.c[1], kTX, kTY);
     const DevParams d = s.dp;
-    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = s.fb_dirty ? 1 : 0;
+    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = (s.fb_dirty && s.sg.dirtyFb) ? 1 : 0;
     auto launch_pvb = [&](int cx0, int cx1, int gapAt, int gapLen) {
       c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
       emu::launch(dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem1, [&] {
-        k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.base[0].p, s.water[0].p,
+        k_fused_pvb(c, d, maps, useTma, s.initial_T.data(), applyPressure, useFb, s.fb.data(), s.dep.data(), s.sg, s.base[0].p, s.water[0].p,
                     s.wall[0].data());
       });
       s.launches++;
@@ -137,13 +142,16 @@ void fused_iteration(Sim& s) {
     derived(s);
     const DevParams d = s.dp;
     emu::launch(dim3((s.ND + 255) / 256, 1), 256, 0, [&] {
-      k_precipitation(s.drops[psrc].data(), s.drops[pdst].data(), s.base[1].p, s.water[1].p, s.fb.data(), s.dep.data(), s.lightning,
+      k_precipitation(s.drops[psrc].data(), s.drops[pdst].data(), s.base[1].p, s.water[1].p, s.fb.data(), s.dep.data(), s.sg, s.lightning,
                       &s.inactive, s.g, d, s.ND);
     });
+    const dim3 tiles(s.sg.tilesX, s.sg.tilesY);
+    emu::launch(tiles, 256, kSmemBox, [&] { k_boxsum(s.sg, s.fb.data(), s.dep.data(), s.W, s.H, s.W); });
+    emu::launch(tiles, 256, 0, [&] { k_clear_origins(s.sg, s.W, s.H); });
     s.fb_dirty = true;
     s.last_drops = pdst;
     emu::launch(dim3(1, 1), 32, 0, [&] { k_latch(s.fb.data(), &s.inactive, s.lightning, d.iterNum, (s.iter % 600 == 0) ? 1 : 0); });
-    s.launches += 2;
+    s.launches += 4;
   }
   s.iter++;
 }
@@ -211,6 +219,26 @@ void ef_upload_drops(void* h, const float* drops, int nd) {
   memset(s.lightning, 0, sizeof(s.lightning));
   std::fill(s.fb.begin(), s.fb.end(), make_float4(0.f, 0.f, 0.f, 0.f));
   std::fill(s.dep.begin(), s.dep.end(), make_float2(0.f, 0.f));
+  // csrc/wsb200.cu: alloc_all / zero_transients for n_droplets > 0
+  SpriteGrid& sg = s.sg;
+  sg.Po = s.W + 1;
+  sg.tilesX = (s.W + kPTX - 1) / kPTX;
+  sg.tilesY = (s.H + kPTY - 1) / kPTY;
+  s.org4.assign((size_t)sg.Po * (s.H + 1), make_float4(0.f, 0.f, 0.f, 0.f));
+  s.org2.assign((size_t)sg.Po * (s.H + 1), make_float2(0.f, 0.f));
+  s.dirtyFb.assign((size_t)sg.tilesX * sg.tilesY, 0);
+  s.dirtyDep.assign((size_t)sg.tilesX * sg.tilesY, 0);
+  sg.org4 = s.org4.data(); sg.org2 = s.org2.data(); sg.dirtyFb = s.dirtyFb.data(); sg.dirtyDep = s.dirtyDep.data();
+}
+// non-zero sprite-origin cells left after a step (k_clear_origins must leave none), and dirty tiles still flagged
+int ef_origin_residue(void* h, int* dirty_tiles) {
+  Sim& s = *(Sim*)h;
+  int n = 0, d = 0;
+  for (const float4& v : s.org4) n += (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f);
+  for (const float2& v : s.org2) n += (v.x != 0.f || v.y != 0.f);
+  for (size_t i = 0; i < s.dirtyFb.size(); i++) d += (s.dirtyFb[i] != 0) || (s.dirtyDep[i] != 0);
+  *dirty_tiles = d;
+  return n;
 }
 void ef_read_drops(void* h, float* dst) { Sim& s = *(Sim*)h; memcpy(dst, s.drops[s.last_drops].data(), (size_t)s.ND * 5 * 4); }
 void ef_read_feedback(void* h, float* fb, float* dep) {

@@ -277,8 +277,8 @@ def test_strip_partition_on_the_emulator_is_bit_identical(emu, ranks, width):
 
 
 def test_particle_pass_on_the_emulator(emu):
-    """k_precipitation (warp-cooperative sprite rasterisation with vector atomics, inactive count per CTA) and
-    k_latch on the emulator: droplet records bit-exact after the first pass, the additive feedback / deposition
+    """k_precipitation (one origin add per droplet, inactive count per CTA), k_boxsum / k_clear_origins (sprites as a
+    12 x 12 box filter over the dirty tiles) and k_latch on the emulator: droplet records bit-exact after the first pass, the additive feedback / deposition
     textures equal up to fp32 summation order, the fields within the north-star tolerance after several iterations
     (the same bars as tests/test_gpu_parity.py)."""
     w, h = 128, 64
@@ -323,6 +323,63 @@ def test_particle_pass_on_the_emulator(emu):
     emu.ef_get_latches(em.h, _ptr(lightning), ctypes.byref(inactive))
     assert np.array_equal(lightning, ora.lightning) and inactive.value == ora.inactive_droplets
     em.close()
+
+
+@pytest.mark.parametrize("shape", [(128, 64), (150, 61), (64, 48)])
+def test_sprite_box_filter_borders_and_overlaps(emu, shape):
+    """Sprites as a box filter of their origins against the oracle's pixel-by-pixel rasterisation: droplets on and
+    next to every border of the viewport (clipped, never wrapped; a centre outside the clip volume is discarded),
+    on tile seams, hundreds overlapping in one spot, droplets in the ground (deposition) — and the origin grid /
+    dirty map must be clean again afterwards (a second pass with all droplets gone leaves only the inactive count)."""
+    w, h = shape
+    g, base, water, wall, _ = stress_state(w, h, seed=9)
+    g["enablePrecipitation"] = True
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([[-1.0, -0.9999, -1.0 + 11.9 / w, 1.0, 0.9999, 1.0 - 11.9 / w, 0.0, 2.0 * 64 / w - 1.0, 2.0 * 63.5 / w - 1.0],
+                         rng.uniform(-1, 1, 300), np.full(200, 0.31), rng.uniform(-1, -0.9, 40), rng.uniform(0.9, 1, 40)])
+    ys = np.concatenate([[0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 0.999, 2.0 * 16 / h - 1.0, 2.0 * 15.5 / h - 1.0],
+                         rng.uniform(-0.99, 0.999, 300), np.full(200, 0.4) + rng.uniform(-0.05, 0.05, 200), rng.uniform(0.9, 0.999, 40),
+                         rng.uniform(-0.999, -0.9, 40)])
+    n = len(xs)
+    drops = np.zeros((n, 5), np.float32)
+    drops[:, 0], drops[:, 1] = xs, ys
+    drops[:, 2] = rng.uniform(0.05, 0.5, n)
+    drops[:, 3] = rng.uniform(0.0, 0.5, n)
+    drops[:, 4] = rng.choice([0.2, 0.6, 1.0], n)
+    ora = make_oracle(g, base, water, wall, drops)
+    em = EmuFused(emu, g, base, water, wall)
+    emu.ef_upload_drops(em.h, _ptr(drops), n)
+    ora.step(1)
+    emu.ef_step(em.h, 1)
+    d = np.empty_like(drops)
+    emu.ef_read_drops(em.h, _ptr(d))
+    fb, dep = np.empty((h, w, 4), np.float32), np.empty((h, w, 2), np.float32)
+    emu.ef_read_feedback(em.h, _ptr(fb), _ptr(dep))
+    assert np.array_equal(d, ora.droplets())
+    want_fb, want_dep = ora.field(O.FIELD_FEEDBACK), ora.field(O.FIELD_DEPOSITION)
+    assert np.array_equal(fb != 0, want_fb != 0) and np.array_equal(dep != 0, want_dep != 0)   # the same texels are covered
+    assert np.allclose(fb, want_fb, rtol=1e-5, atol=1e-7) and np.allclose(dep, want_dep, rtol=1e-5, atol=1e-7)
+    assert (want_dep != 0).any() and (want_fb[:, 0] != 0).any() and (want_fb[:, -1] != 0).any() and (want_fb[-1] != 0).any()
+    assert np.abs(want_fb[..., 0]).max() > 50 * np.abs(want_fb[..., 0][want_fb[..., 0] != 0]).min()   # a pile of overlapping sprites
+    dirty = ctypes.c_int()
+    assert emu.ef_origin_residue(em.h, ctypes.byref(dirty)) == 0 and dirty.value > 0   # origins cleared; tiles await the boundary kernel
+    emu.ef_step(em.h, 1)                                                                 # ... which consumes and clears them, before the next pass flags its own
+    # second pass: deactivate every droplet; feedback must then hold the inactive count and nothing else
+    ora.step(1)
+    gone = ora.droplets().copy()
+    gone[:, 2] = -5.0
+    ora.droplets(copy=False)[...] = gone
+    emu.ef_upload_drops(em.h, _ptr(gone), n)   # also clears feedback / deposition like the reference's gl.clear
+    p = P.derive_params(g)
+    p.spawnChanceMult = 0.0
+    ora.set_params(p)
+    emu.ef_set_params(em.h, ctypes.byref(p))
+    ora.field(O.FIELD_FEEDBACK, copy=False)[...] = 0
+    ora.field(O.FIELD_DEPOSITION, copy=False)[...] = 0
+    ora.run_pass(7)
+    emu.ef_step(em.h, 1)
+    emu.ef_read_feedback(em.h, _ptr(fb), _ptr(dep))
+    assert fb[0, 0, 0] == n and np.count_nonzero(fb) == 1 and not dep.any()
 
 
 def test_fused_kernels_on_the_emulator_forcing_and_slow_processes(emu):
