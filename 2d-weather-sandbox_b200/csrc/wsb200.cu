@@ -167,11 +167,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 // spin until *flag >= seq (sequence numbers wrap: compare as a signed difference)
+__device__ unsigned g_pollNs = 100;  // back-off between two polls (WSB_DBG_POLL_NS: experiments)
 __device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned seq, unsigned* err, unsigned long long limitNs) {
   const unsigned long long t0 = global_ns();
+  const unsigned pollNs = g_pollNs;
   while ((int)(ld_acquire_sys(flag) - seq) < 0) {
     if (global_ns() - t0 > limitNs) { atomicExch(err, 1u); return; }
-    __nanosleep(100);
+    __nanosleep(pollNs);
   }
 }
 
@@ -224,9 +226,12 @@ __global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ Pus
       for (int i = 0; i < 4; i++) { dl[i] = sL[i]; dr[i] = sR[i]; }
     }
   }
-  __threadfence_system();
+  // one system-scope fence per BLOCK: the barrier orders the block's stores before thread 0's fence (fence cumulativity,
+  // the pattern of cooperative-groups grid sync); a fence in every thread (592 warps x membar.sys) measurably slowed
+  // the advection kernel running beside this one (profiles/r3_multi_gpu.md)
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned* done = myFlags + kFlagBlocks * kFlagStride;
     if (atomicAdd(done, 1u) == gridDim.x - 1) {  // last block: every block's stores are visible system-wide
       *done = 0u;
@@ -288,6 +293,8 @@ struct wsb_sim {
   bool use_tma = false;
   float4* fb = nullptr;
   float2 *dep = nullptr, *vort = nullptr;
+  unsigned char* dry_tilewalls = nullptr;  // k_fused_dry: one byte per 64 x 28 tile, "a wall cell in the staged region" (k_wall_tilemap)
+  bool dry_tilewalls_valid = false;        // false whenever the wall texture may have changed
   SpriteGrid sg{};  // sprite origins + dirty-tile map of the particle pass (single GPU, n_droplets > 0)
   float* curl = nullptr;
   float* drops[2] = {};
@@ -331,6 +338,9 @@ struct wsb_sim {
   int pitchL = 0, pitchR = 0, lwL = 0;
   unsigned xseq = 0, pending_seq = 0;       // exchanges issued / the one in flight
   unsigned long long spin_ns = kSpinLimitNs;
+  int n_sms = 148;
+  int push_blocks = 37;                     // WSB_DBG_PUSH_BLOCKS
+  bool dbg_nopush = false;                  // WSB_DBG_NOPUSH: timing experiments only — ghost columns are never refreshed
   cudaEvent_t evEdge = nullptr, evPush = nullptr, evPvbI = nullptr, evPvbE = nullptr, evAdvI = nullptr;
   bool push_pending = false;                // a k_push_ghosts is reading this rank's edge columns
   int pvbInnerEnd = 0, advEdgeStart = 0;    // tile-column split of the strip (local columns)
@@ -408,6 +418,7 @@ void add_wall(XPlanes& x, const wsb_sim* s, int k) {
 // Peer transport: on the communication stream, after whatever the caller has ordered there — the handshake kernel,
 // then the copy of this rank's outermost owned columns into the neighbours' ghost columns.
 int push_ghosts(wsb_sim* s, const XPlanes& xp) {
+  if (s->dbg_nopush) return 0;
   cudaStream_t cs = s->comm_stream;
   const HaloPlanes& hp = xp.hp;
   ProfScope prof(s, WSB_KERNEL_HALO, cs);
@@ -423,7 +434,7 @@ int push_ghosts(wsb_sim* s, const XPlanes& xp) {
   a.spinNs = s->spin_ns;
   k_ghosts_free<<<1, 1, 0, cs>>>(a);
   LAUNCHED("k_ghosts_free");
-  const int threads = 256, blocks = std::min(74, (hp.n * s->H * 2 + threads - 1) / threads);  // short-lived, half an SM wave
+  const int threads = 256, blocks = std::min(s->push_blocks, (hp.n * s->H * 2 + threads - 1) / threads);  // short-lived, a fraction of an SM wave
   k_push_ghosts<<<blocks, threads, 0, cs>>>(a);
   LAUNCHED("k_push_ghosts");
   CK(cudaEventRecord(s->evPush, cs));
@@ -553,10 +564,7 @@ int clear_feedback(wsb_sim* s) {
   if (!s->fb_dirty) return 0;
   CK(cudaMemsetAsync(s->fb, 0, cells(s) * sizeof(float4), s->stream));
   CK(cudaMemsetAsync(s->dep, 0, cells(s) * sizeof(float2), s->stream));
-  if (s->sg.dirtyFb) {
-    CK(cudaMemsetAsync(s->sg.dirtyFb, 0, (size_t)s->sg.tilesX * s->sg.tilesY, s->stream));
-    CK(cudaMemsetAsync(s->sg.dirtyDep, 0, (size_t)s->sg.tilesX * s->sg.tilesY, s->stream));
-  }
+  if (s->sg.dirty) CK(cudaMemsetAsync(s->sg.dirty, 0, (size_t)s->sg.tilesX * s->sg.tilesY * sizeof(int), s->stream));
   s->launches += 2;
   s->fb_dirty = false;
   return 0;
@@ -574,12 +582,14 @@ int precipitation(wsb_sim* s) {
   k_precipitation<<<blocks, threads, 0, s->stream>>>(s->drops[src], s->drops[dst], s->base[1].p, s->water[1].p, s->fb, s->dep, s->sg,
                                                      s->lightning, s->inactive, s->g, s->dp, s->ND);
   LAUNCHED("k_precipitation");
-  // sprites = 12 x 12 box filter of the origins, on the tiles that were touched
-  const dim3 tiles(s->sg.tilesX, s->sg.tilesY);
-  k_boxsum<<<tiles, 256, kSmemBox, s->stream>>>(s->sg, s->fb, s->dep, s->W, s->H, s->pitch);
-  LAUNCHED("k_boxsum");
-  k_clear_origins<<<tiles, 256, 0, s->stream>>>(s->sg, s->W, s->H);
-  LAUNCHED("k_clear_origins");
+  {  // sprites = 12 x 12 box filter of the origins, on the tiles that were touched
+    ProfScope profSprites(s, WSB_KERNEL_SPRITES);
+    const int ctas = std::min(s->n_sms * 3, s->sg.tilesX * s->sg.tilesY);  // persistent: the list of touched tiles is walked on the device
+    k_boxsum<<<ctas, 256, kSmemBox, s->stream>>>(s->sg, s->fb, s->dep, s->W, s->H, s->pitch);
+    LAUNCHED("k_boxsum");
+    k_clear_origins<<<ctas, 256, 0, s->stream>>>(s->sg, s->W, s->H, reinterpret_cast<unsigned*>(s->sg.dirtyCount + 1));
+    LAUNCHED("k_clear_origins");
+  }
   s->fb_dirty = true;
   s->last_drops = dst;
   k_latch<<<1, 32, 0, s->stream>>>(s->fb, s->inactive, s->lightning, s->dp.iterNum, (s->iter % 600 == 0) ? 1 : 0);
@@ -588,6 +598,7 @@ int precipitation(wsb_sim* s) {
 }
 
 int ref_iteration(wsb_sim* s) {
+  s->dry_tilewalls_valid = false;
   if (ref_velocity(s) || ref_curl(s) || ref_vorticity(s) || ref_boundary(s) || ref_advection(s, false) ||
       ref_pressure(s) || ref_lighting(s) || clear_feedback(s) || precipitation(s))
     return 1;
@@ -611,7 +622,7 @@ int launch_pvb(wsb_sim* s, cudaStream_t st, int cx0, int cx1, int gapAt, int gap
   maps.m[10] = s->light[0].map0[1];  // NET_HEATING
   c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
   k_fused_pvb<<<dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s->H + kTY - 1) / kTY), kNT, kSmem1, st>>>(
-      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, (s->fb_dirty && s->sg.dirtyFb) ? 1 : 0, s->fb, s->dep,
+      c, s->dp, maps, s->use_tma ? 1 : 0, s->initial_T, s->pressure_pending ? 1 : 0, (s->fb_dirty && s->sg.dirty) ? 1 : 0, s->fb, s->dep,
       s->sg, s->base[0].p, s->water[0].p, s->wall[0]);
   return check_launch(s, "k_fused_pvb");
 }
@@ -693,6 +704,7 @@ int fused_iteration_overlapped(wsb_sim* s) {
 }
 
 int fused_iteration(wsb_sim* s) {
+  s->dry_tilewalls_valid = false;  // boundary / advection rewrite the wall texture
   if (s->peer_mode && s->pvbInnerEnd > kTX && s->advEdgeStart > kTX) return fused_iteration_overlapped(s);
   set_iter_uniform(s);
   const int src = s->even ? 0 : 1, dst = s->even ? 1 : 0;
@@ -744,12 +756,18 @@ int dry_iteration(wsb_sim* s) {
   } else {
     // same canonical state as the full fused schedule: base_1 = advection output, pressure pending
     {
+      const dim3 tiles((s->pitch + kTX - 1) / kTX, (s->H + kTYD - 1) / kTYD);
+      if (!s->dry_tilewalls_valid) {  // the dry sweep itself never changes the wall texture
+        k_wall_tilemap<<<tiles, 256, 0, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dry_tilewalls);
+        LAUNCHED("k_wall_tilemap");
+        s->dry_tilewalls_valid = true;
+      }
       ProfScope prof(s, WSB_KERNEL_DRY);
       TileMaps<5> maps;
       for (int k = 0; k < 4; k++) maps.m[k] = s->base[1].mapD[k];
       maps.m[4] = s->wallMapD[1];
-      k_fused_dry<<<dim3((s->pitch + kTX - 1) / kTX, (s->H + kTYD - 1) / kTYD), kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0,
-                                                               s->pressure_pending ? 1 : 0, s->base[0].p, s->maxv);
+      k_fused_dry<<<tiles, kNT, kSmemDry, s->stream>>>(make_ctx(s, 1, 1, 1, 0), s->dp, maps, s->use_tma ? 1 : 0, s->pressure_pending ? 1 : 0,
+                                                       s->dry_tilewalls, s->base[0].p, s->maxv);
       LAUNCHED("k_fused_dry");
     }
     std::swap(s->base[0], s->base[1]);
@@ -837,8 +855,9 @@ int alloc_all(wsb_sim* s) {
     const size_t no = (size_t)sg.Po * (s->H + 1), nt = (size_t)sg.tilesX * sg.tilesY;
     CK(cudaMalloc(&sg.org4, no * sizeof(float4)));
     CK(cudaMalloc(&sg.org2, no * sizeof(float2)));
-    CK(cudaMalloc(&sg.dirtyFb, nt));
-    CK(cudaMalloc(&sg.dirtyDep, nt));
+    CK(cudaMalloc(&sg.dirty, nt * sizeof(int)));
+    CK(cudaMalloc(&sg.dirtyList, nt * sizeof(int)));
+    CK(cudaMalloc(&sg.dirtyCount, 2 * sizeof(int)));  // [1]: CTA counter of k_clear_origins
   }
   if (s->schedule == WSB_SCHEDULE_REFERENCE) {
     CK(cudaMalloc(&s->curl, n * sizeof(float)));
@@ -853,6 +872,7 @@ int alloc_all(wsb_sim* s) {
   CK(cudaMemset(s->sndT, 0, np * 4));
   CK(cudaMemset(s->sndW, 0, np * 4));
   CK(cudaMemset(s->sndV, 0, np * 4));
+  CK(cudaMalloc(&s->dry_tilewalls, (size_t)((s->pitch + kTX - 1) / kTX) * ((s->H + kTYD - 1) / kTYD)));
   CK(cudaMalloc(&s->lightning, 16));
   CK(cudaMalloc(&s->inactive, 4));
   CK(cudaMalloc(&s->maxv, 4));
@@ -888,8 +908,8 @@ int zero_transients(wsb_sim* s) {
     const size_t no = (size_t)s->sg.Po * (s->H + 1), nt = (size_t)s->sg.tilesX * s->sg.tilesY;
     CK(cudaMemsetAsync(s->sg.org4, 0, no * sizeof(float4), s->stream));
     CK(cudaMemsetAsync(s->sg.org2, 0, no * sizeof(float2), s->stream));
-    CK(cudaMemsetAsync(s->sg.dirtyFb, 0, nt, s->stream));
-    CK(cudaMemsetAsync(s->sg.dirtyDep, 0, nt, s->stream));
+    CK(cudaMemsetAsync(s->sg.dirty, 0, nt * sizeof(int), s->stream));
+    CK(cudaMemsetAsync(s->sg.dirtyCount, 0, 2 * sizeof(int), s->stream));
   }
   if (s->curl) CK(cudaMemsetAsync(s->curl, 0, n * sizeof(float), s->stream));
   if (s->vort) CK(cudaMemsetAsync(s->vort, 0, n * sizeof(float2), s->stream));
@@ -901,6 +921,7 @@ int zero_transients(wsb_sim* s) {
   s->last_drops = 0;
   s->pressure_pending = false;
   s->fb_dirty = false;
+  s->dry_tilewalls_valid = false;
   return 0;
 }
 
@@ -1059,7 +1080,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
        // synchronise the context — behind a neighbour's spinning k_push_ghosts / k_wait_ghosts that would stall
        // (several strips in one process: deadlock until the bounded wait runs out).
       cudaFuncAttributes fa;
-      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_push_ghosts, (const void*)k_ghosts_free,
+      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_wall_tilemap, (const void*)k_push_ghosts, (const void*)k_ghosts_free,
                            (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation, (const void*)k_boxsum, (const void*)k_clear_origins,
                            (const void*)k_latch, (const void*)k_texels_to_planes, (const void*)k_planes_to_texels, (const void*)k_pressure_rect,
                            (const void*)k_gather_points};
@@ -1067,6 +1088,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
         if ((e = cudaFuncGetAttributes(&fa, f)) != cudaSuccess) break;
       if (e != cudaSuccess) { rc = fail("wsb_create: kernels not loadable on this device (built for sm_100a): %s", cudaGetErrorString(e)); break; }
     }
+    cudaDeviceGetAttribute(&s->n_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     if ((rc = alloc_all(s))) break;
     if ((rc = zero_transients(s))) break;
     if (cfg->n_ranks > 1) {
@@ -1082,6 +1104,12 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
           (e = cudaEventCreateWithFlags(&s->evAdvI, cudaEventDisableTiming)) != cudaSuccess) {
         rc = fail("wsb_create: %s", cudaGetErrorString(e));
         break;
+      }
+      if (const char* v = getenv("WSB_DBG_NOPUSH")) s->dbg_nopush = atoi(v) != 0;
+      if (const char* v = getenv("WSB_DBG_PUSH_BLOCKS")) s->push_blocks = std::max(1, atoi(v));
+      if (const char* v = getenv("WSB_DBG_POLL_NS")) {
+        const unsigned ns = (unsigned)atoi(v);
+        cudaMemcpyToSymbol(g_pollNs, &ns, sizeof ns);
       }
       if (const char* lim = getenv("WSB_SPIN_LIMIT_MS")) {
         const long ms = atol(lim);
@@ -1130,8 +1158,9 @@ int wsb_destroy(wsb_sim* s) {
   if (s->evPvbE) cudaEventDestroy(s->evPvbE);
   if (s->evAdvI) cudaEventDestroy(s->evAdvI);
   cudaFree(s->fb); cudaFree(s->dep); cudaFree(s->curl); cudaFree(s->vort);
-  cudaFree(s->sg.org4); cudaFree(s->sg.org2); cudaFree(s->sg.dirtyFb); cudaFree(s->sg.dirtyDep);
+  cudaFree(s->sg.org4); cudaFree(s->sg.org2); cudaFree(s->sg.dirty); cudaFree(s->sg.dirtyList); cudaFree(s->sg.dirtyCount);
   cudaFree(s->initial_T); cudaFree(s->sndT); cudaFree(s->sndW); cudaFree(s->sndV);
+  cudaFree(s->dry_tilewalls);
   cudaFree(s->lightning); cudaFree(s->inactive); cudaFree(s->maxv); cudaFree(s->scratch);
   cudaFree(s->sendL); cudaFree(s->sendR); cudaFree(s->recvL); cudaFree(s->recvR);
   for (cudaEvent_t e : s->ev_pool) cudaEventDestroy(e);
@@ -1318,6 +1347,7 @@ int wsb_connect_peers(wsb_sim* s, const uint8_t* left, const uint8_t* right) {
 
 int wsb_debug_run_pass(wsb_sim* s, int32_t pass) {
   if (!s) return fail("wsb_debug_run_pass: null sim");
+  s->dry_tilewalls_valid = false;
   if (s->schedule != WSB_SCHEDULE_REFERENCE) return fail("wsb_debug_run_pass needs WSB_SCHEDULE_REFERENCE");
   if (use_device(s)) return 1;
   switch (pass) {
@@ -1505,7 +1535,7 @@ int wsb_set_profiling(wsb_sim* s, int32_t on) {
 
 int wsb_kernel_time_ms(wsb_sim* s, int32_t kernel, float* total_ms, int32_t* launches) {
   if (!s || !total_ms || !launches) return fail("wsb_kernel_time_ms: null argument");
-  if (kernel < 0 || kernel > WSB_KERNEL_EDGE) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
+  if (kernel < 0 || kernel > WSB_KERNEL_SPRITES) return fail("wsb_kernel_time_ms: unknown kernel class %d", kernel);
   if (use_device(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
   double sum = 0.0;

@@ -53,11 +53,14 @@ constexpr int kHX = 4;
 struct SpriteGrid {
   float4* org4;          // feedback origins
   float2* org2;          // deposition origins
-  unsigned char* dirtyFb;   // [tilesY][tilesX]: a sprite (or a direct 1-pixel add) touched this tile's feedback texels
-  unsigned char* dirtyDep;  // ... deposition texels
+  int* dirty;            // [tilesY][tilesX] bit 0: a sprite (or a direct 1-pixel add) touched this tile's feedback texels,
+                         //                  bit 1: ... its deposition texels.  Set by the particle pass, cleared by the boundary kernel
+  int* dirtyList;        // the tiles whose word went 0 -> non-zero in this particle pass, in arrival order ...
+  int* dirtyCount;       // ... and how many (k_boxsum / k_clear_origins walk the list; the latter resets the count)
   int Po;                // origin row pitch = W + 1
   int tilesX, tilesY;
 };
+enum { kDirtyFb = 1, kDirtyDep = 2 };
 
 // ---------------------------------------------------------------------------------------------
 // Tile staging
@@ -279,84 +282,32 @@ __device__ __forceinline__ WallMix tile_wall_mix(const int* sWl, int l, float fx
 }
 
 // ---- stencil sweeps over the staged planes ------------------------------------------------------
-// Two variants, same arithmetic: PAIR (two horizontally adjacent cells per thread, 8-byte accesses)
-// and QUAD (four cells, 16-byte accesses).  QUAD executes ~25 % fewer instructions, but the sweeps
-// are bound by shared-memory wavefronts and by how many warps have work between two barriers, not
-// by issue slots: measured on the dry sweep (profiles/r2_dry_variants.md) PAIR is 7 % faster, so it
-// is the default.  Row strides and plane sizes are multiples of 4 floats and planes are 128-byte
-// aligned, so an even index is 8-byte and a multiple of 4 is 16-byte aligned.
-#ifndef WSB_SWEEP_QUAD
-#define WSB_SWEEP_QUAD 0
-#endif
+// Two horizontally adjacent cells per thread, 8-byte accesses.  (A four-cell / 16-byte variant executes ~25 % fewer
+// instructions but measured 7 % SLOWER on the dry sweep, profiles/r2_dry_variants.md: the sweeps are bound by
+// shared-memory wavefronts and by how many warps have work between two barriers, not by issue slots.)  Row strides and
+// plane sizes are multiples of 4 floats and planes are 128-byte aligned, so an even index is 8-byte aligned.
+// WALLS = false: the staged region is known to hold no wall cell (k_fused_dry's tile map): no wall plane is staged,
+// the land-wall rule of the pressure pass cannot fire (T' == T, nothing to write) and every cell is fluid.
 __device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ int2 ld2(const int* p) { return *reinterpret_cast<const int2*>(p); }
 __device__ __forceinline__ void st2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ int4 ld4(const int* p) { return *reinterpret_cast<const int4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-#if WSB_SWEEP_QUAD
 // pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
 // P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
-template <int SW, int N>
+template <int SW, int N, bool WALLS = true>
 __device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sVY, float* sP, const float* sT, float* sT2,
                                                const int* sWl, int applyPressure) {
-  static_assert(SW % 4 == 0 && N % 4 == 0, "quad sweeps need rows of whole quads");
-  for (int s = SW + 4 * (int)threadIdx.x; s < N; s += 4 * kNT) {
-    float4 T = ld4(sT + s);
-    if (applyPressure) {
-      const int4 wb = ld4(sWl + s - SW);
-      const float4 Tb = ld4(sT + s - SW);
-      if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
-      if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
-      if (wl_is_land_wall(wb.z)) T.z -= Tb.z - 1000.0f;
-      if (wl_is_land_wall(wb.w)) T.w -= Tb.w - 1000.0f;
-      const float4 vx = ld4(sVX + s), vy = ld4(sVY + s), vyb = ld4(sVY + s - SW);
-      const float vxm = sVX[s - 1];
-      float4 P = ld4(sP + s);
-      P.x += (vxm - vx.x + vyb.x - vy.x) * 0.45f;
-      P.y += (vx.x - vx.y + vyb.y - vy.y) * 0.45f;
-      P.z += (vx.y - vx.z + vyb.z - vy.z) * 0.45f;
-      P.w += (vx.z - vx.w + vyb.w - vy.w) * 0.45f;
-      st4(sP + s, P);
-    }
-    st4(sT2 + s, T);
-  }
-}
-// velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
-template <int SW, int N>
-__device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl,
-                                               unsigned* sAnyWall = nullptr) {
-  bool any = false;
-  for (int s = SW + 4 * (int)threadIdx.x; s < N - SW; s += 4 * kNT) {
-    float4 vx = ld4(sVX + s), vy = ld4(sVY + s);
-    const float4 P = ld4(sP + s), Pu = ld4(sP + s + SW);
-    const float Pr = sP[s + 4];
-    const int4 w = ld4(sWl + s);
-    velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wl_is_wall(w.x) ? 0 : 1);
-    velocity_cell(d, vx.y, vy.y, P.y, P.z, Pu.y, wl_is_wall(w.y) ? 0 : 1);
-    velocity_cell(d, vx.z, vy.z, P.z, P.w, Pu.z, wl_is_wall(w.z) ? 0 : 1);
-    velocity_cell(d, vx.w, vy.w, P.w, Pr, Pu.w, wl_is_wall(w.w) ? 0 : 1);
-    any |= wl_is_wall(w.x) | wl_is_wall(w.y) | wl_is_wall(w.z) | wl_is_wall(w.w);
-    st4(sVX + s, vx);
-    st4(sVY + s, vy);
-  }
-  if (sAnyWall && __any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *sAnyWall = 1u;
-}
-
-#else
-// pressure pass of the previous iteration (pressureShader.frag:24-42); valid for i >= 1, j >= 1.
-// P' only reads velocities: in place.  T' reads the raw T below: written to sT2.
-template <int SW, int N>
-__device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sVY, float* sP, const float* sT, float* sT2,
-                                               const int* sWl, int applyPressure) {
+  if (!WALLS && !applyPressure) return;
   for (int s = SW + 2 * (int)threadIdx.x; s < N; s += 2 * kNT) {
-    float2 T = ld2(sT + s);
+    float2 T;
+    if (WALLS) T = ld2(sT + s);
     if (applyPressure) {
-      const int2 wb = ld2(sWl + s - SW);
-      const float2 Tb = ld2(sT + s - SW);
-      if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
-      if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
+      if (WALLS) {
+        const int2 wb = ld2(sWl + s - SW);
+        const float2 Tb = ld2(sT + s - SW);
+        if (wl_is_land_wall(wb.x)) T.x -= Tb.x - 1000.0f;
+        if (wl_is_land_wall(wb.y)) T.y -= Tb.y - 1000.0f;
+      }
       const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vyb = ld2(sVY + s - SW);
       const float vxm = sVX[s - 1];
       float2 P = ld2(sP + s);
@@ -364,13 +315,13 @@ __device__ __forceinline__ void sweep_pressure(const float* sVX, const float* sV
       P.y += (vx.x - vx.y + vyb.y - vy.y) * 0.45f;
       st2(sP + s, P);
     }
-    st2(sT2 + s, T);
+    if (WALLS) st2(sT2 + s, T);
   }
 }
 // velocity pass (velocityShader.frag:40-61), in place; valid for 1 <= i <= SW-2, 1 <= j <= SH-2
 // sAnyWall (optional, zeroed by the caller before an earlier barrier): set to 1 when any cell of
 // the swept rows is a wall, so that the per-cell pass can drop its wall tests on all-air tiles.
-template <int SW, int N>
+template <int SW, int N, bool WALLS = true>
 __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, float* sVY, const float* sP, const int* sWl,
                                                unsigned* sAnyWall = nullptr) {
   bool any = false;
@@ -378,8 +329,12 @@ __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, f
     float2 vx = ld2(sVX + s), vy = ld2(sVY + s);
     const float2 P = ld2(sP + s), Pu = ld2(sP + s + SW);
     const float Pr = sP[s + 2];
-    const int2 w = ld2(sWl + s);
-    const bool wa = wl_is_wall(w.x), wb = wl_is_wall(w.y);
+    bool wa = false, wb = false;
+    if (WALLS) {
+      const int2 w = ld2(sWl + s);
+      wa = wl_is_wall(w.x);
+      wb = wl_is_wall(w.y);
+    }
     any |= wa | wb;
     velocity_cell(d, vx.x, vy.x, P.x, P.y, Pu.x, wa ? 0 : 1);
     velocity_cell(d, vx.y, vy.y, P.y, Pr, Pu.y, wb ? 0 : 1);
@@ -388,8 +343,6 @@ __device__ __forceinline__ void sweep_velocity(const DevParams& d, float* sVX, f
   }
   if (sAnyWall && __any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) *sAnyWall = 1u;
 }
-
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // k_fused_dry — pressure(prev) -> velocity -> advection(base): BASELINE config 2 / headline sweep
@@ -425,7 +378,8 @@ constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;
 __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_constant__ GlobalCtx glob,
                                                       const __grid_constant__ DevParams d,
                                                       const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
-                                                      Planes4 baseOut, unsigned* __restrict__ maxv) {
+                                                      const unsigned char* __restrict__ tileWalls, Planes4 baseOut,
+                                                      unsigned* __restrict__ maxv) {
   WSB_DYN_SMEM(smem_raw);
   float* sVX = reinterpret_cast<float*>(smem_raw);
   float* sVY = sVX + kPSD;
@@ -442,23 +396,28 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
   const int tid = threadIdx.x;
   const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTYD - kHD;
 
+  // tileWalls[tile] == 0: no wall cell anywhere in this tile's staged region (k_wall_tilemap; the dry sweep never
+  // changes the wall texture, so the map stays valid between wall-changing calls).  Such tiles — all of the free
+  // atmosphere — do not stage the wall plane at all (16 of 20 staged bytes per cell, 32 of 36 B / cell of HBM traffic),
+  // their sweeps skip the wall tests and the land-wall rule of the pressure pass (T' == T).
+  const bool walls = tileWalls == nullptr || tileWalls[blockIdx.y * gridDim.x + blockIdx.x] != 0;
   if (tid == 0) { *sMax = 0u; *sAnyWall = 0u; }
   if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(mbar, 5u * kND * 4u);
+      mbar_expect_tx(mbar, (walls ? 5u : 4u) * kND * 4u);
       tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
       tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
       tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
       tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
-      tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
+      if (walls) tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
     }
     mbar_wait(mbar, 0);
   } else {
     stage_tile<kSWD, kSHD, 6>(
         g, X0, Y0,
-        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], glob.wall[ci]}; },
+        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], walls ? glob.wall[ci] : 0x0100}; },
         [&](int s, const BaseWallRegs& r) {
           sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
           sWl[s] = r.w;
@@ -466,19 +425,24 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
     __syncthreads();
   }
 
-  sweep_pressure<kSWD, kND>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
+  if (walls) {
+    sweep_pressure<kSWD, kND, true>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
+    __syncthreads();
+    sweep_velocity<kSWD, kND, true>(d, sVX, sVY, sP, sWl);
+  } else {
+    sweep_pressure<kSWD, kND, false>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
+    __syncthreads();
+    sweep_velocity<kSWD, kND, false>(d, sVX, sVY, sP, sWl);
+  }
   __syncthreads();
-  sweep_velocity<kSWD, kND>(d, sVX, sVY, sP, sWl, sAnyWall);
-  __syncthreads();
-
-  // advection of the base field on the tile.  On an all-air tile (most of the atmosphere) the own
-  // cell's wall test and the wall-aware bilerp weights fall away: every tap of a near back-trace
-  // lies in the rows the velocity sweep has just looked at.
-#if WSB_OPT_AIRFAST
-  const bool walls = *sAnyWall != 0u;
+#if WSB_OPT_NEAR
+  const int tPlane = walls ? 5 * kPSD : 3 * kPSD;   // T after the pressure pass, as a displacement from the VX plane
 #else
-  const bool walls = true;
+  const float* sTpost = walls ? sT2 : sT;
 #endif
+
+  // advection of the base field on the tile.  On an all-air tile the own cell's wall test and the wall-aware
+  // bilerp weights fall away: every tap of a near back-trace lies in the staged region.
   float vm = 0.0f;
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
@@ -518,7 +482,7 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
           const WallMix m = walls ? tile_wall_mix<SW>(reinterpret_cast<const int*>(q3 + 4 * kPSD), 0, n3.fx, n3.fy)
                                   : WallMix{n3.fx, n3.fx, n3.fy};
           const float* qP = q3 + 2 * kPSD;
-          const float* qT = q3 + 5 * kPSD;
+          const float* qT = q3 + tPlane;
           base.z = mix2d(qP[0], qP[1], qP[SW], qP[SW + 1], m.ab, m.cd, m.abcd);
           base.w = mix2d(qT[0], qT[1], qT[SW], qT[SW + 1], m.ab, m.cd, m.abcd);
         } else {  // |v| >= 0.9 cells / iteration (never seen in the shipped saves): exact global-memory path
@@ -538,9 +502,9 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
         if (tile_ok<kSWD, kSHD>(lx1, ly1, 1, 1) && tile_ok<kSWD, kSHD>(lx2, ly2, 1, 1) && tile_ok<kSWD, kSHD>(lx3, ly3, 1, 1)) {
           base.x = mix2d(sVX[l1], sVX[l1 + 1], sVX[l1 + SW], sVX[l1 + SW + 1], b1.fx, b1.fx, b1.fy);
           base.y = mix2d(sVY[l2], sVY[l2 + 1], sVY[l2 + SW], sVY[l2 + SW + 1], b2.fx, b2.fx, b2.fy);
-          const WallMix m = tile_wall_mix<SW>(sWl, l3, b3.fx, b3.fy);
+          const WallMix m = walls ? tile_wall_mix<SW>(sWl, l3, b3.fx, b3.fy) : WallMix{b3.fx, b3.fx, b3.fy};
           base.z = mix2d(sP[l3], sP[l3 + 1], sP[l3 + SW], sP[l3 + SW + 1], m.ab, m.cd, m.abcd);
-          base.w = mix2d(sT2[l3], sT2[l3 + 1], sT2[l3 + SW], sT2[l3 + SW + 1], m.ab, m.cd, m.abcd);
+          base.w = mix2d(sTpost[l3], sTpost[l3 + 1], sTpost[l3 + SW], sTpost[l3 + SW + 1], m.ab, m.cd, m.abcd);
         } else {
           float vmSlow = 0.0f;
           base = dry_advect_slow(&glob, &d, applyPressure, x, y, &vmSlow);
@@ -555,6 +519,21 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
   }
   if (x < g.ox0 || x >= g.ox1) vm = 0.0f;  // ghost columns hold the neighbour's cells (and edge garbage)
   report_vmax_cta(vm, maxv, sMax);
+}
+
+// One byte per dry-sweep tile: does its staged region (tile + halo, periodic in x and y like the textures) hold a wall
+// cell?  Recomputed (4 B / cell, once) when the wall texture may have changed: upload, any full-physics iteration.
+__global__ void k_wall_tilemap(GlobalCtx glob, unsigned char* __restrict__ tileWalls) {
+  const Geom& g = glob.g;
+  const int X0 = blockIdx.x * kTX - kHX, Y0 = blockIdx.y * kTYD - kHD;
+  bool any = false;
+  for (int i = threadIdx.x; i < kND; i += blockDim.x) {
+    const int j = i / kSWD, ii = i - j * kSWD;
+    const int x = wrap_x(g, X0 + ii), y = wrap_y(Y0 + j, g.H);
+    any |= wl_is_wall(glob.wall[(size_t)y * g.pitch + x]);
+  }
+  const int r = __syncthreads_or(any ? 1 : 0);
+  if (threadIdx.x == 0) tileWalls[blockIdx.y * gridDim.x + blockIdx.x] = r ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -643,7 +622,8 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   const bool colOk = x < g.cx1;
   // feedback / deposition of the last particle pass: only tiles a sprite touched hold anything
   const int dirtyIdx = blockIdx.y * sg.tilesX + (X0 + kHX) / kTX;
-  const bool tileFb = useFb && sg.dirtyFb[dirtyIdx] != 0, tileDep = useFb && sg.dirtyDep[dirtyIdx] != 0;
+  const int dirtyBits = useFb ? sg.dirty[dirtyIdx] : 0;
+  const bool tileFb = (dirtyBits & kDirtyFb) != 0, tileDep = (dirtyBits & kDirtyDep) != 0;
 
   if (tile_tma_ok<kSW1, kSH1>(g, useTma, X0, Y0)) {
     if (tid == 0) mbar_init(mbar, 1);
@@ -684,27 +664,6 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
   __syncthreads();
   sweep_velocity<kSW1, kN1>(d, sVX, sVY, sP, sWl);
   __syncthreads();
-#if WSB_SWEEP_QUAD
-  // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
-  for (int s = SW + 4 * tid; s < kN1 - 2 * SW; s += 4 * kNT) {
-    const float4 vx = ld4(sVX + s), vy = ld4(sVY + s), vxu = ld4(sVX + s + SW);
-    const float vyr = sVY[s + 4];
-    st4(sCurl + s, make_float4(curl_cell(vx.x, vy.x, vxu.x, vy.y), curl_cell(vx.y, vy.y, vxu.y, vy.z),
-                               curl_cell(vx.z, vy.z, vxu.z, vy.w), curl_cell(vx.w, vy.w, vxu.w, vyr)));
-  }
-  __syncthreads();
-  // S4: vorticity force on the rows the boundary pass reads (tile rows and the row below them);
-  // valid for 2 <= i <= SW-4
-  for (int s = (kH1 - 1) * SW + 4 * tid; s < (kH1 + kTY) * SW; s += 4 * kNT) {
-    const float4 c = ld4(sCurl + s), cd = ld4(sCurl + s - SW), cu = ld4(sCurl + s + SW);
-    const float cl = sCurl[s - 1], cr = sCurl[s + 4];
-    const float2 v0 = vorticity_cell(c.x, cl, cd.x, c.y, cu.x), v1 = vorticity_cell(c.y, c.x, cd.y, c.z, cu.y),
-                 v2 = vorticity_cell(c.z, c.y, cd.z, c.w, cu.z), v3 = vorticity_cell(c.w, c.z, cd.w, cr, cu.w);
-    st4(sVFX + s - (kH1 - 1) * SW, make_float4(v0.x, v1.x, v2.x, v3.x));
-    st4(sVFY + s - (kH1 - 1) * SW, make_float4(v0.y, v1.y, v2.y, v3.y));
-  }
-  __syncthreads();
-#else
   // S3: curl; valid for 1 <= i <= SW-3, 1 <= j <= SH-3 (raw T plane is dead: reuse it)
   for (int s = SW + 2 * tid; s < kN1 - 2 * SW; s += 2 * kNT) {
     const float2 vx = ld2(sVX + s), vy = ld2(sVY + s), vxu = ld2(sVX + s + SW);
@@ -722,7 +681,6 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
     st2(sVFY + s - (kH1 - 1) * SW, make_float2(va.y, vb.y));
   }
   __syncthreads();
-#endif
 
   // S5: boundary pass on the TX x TY interior
 #pragma unroll 1
@@ -745,10 +703,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_pvb(const __grid_constant__ Gl
       if (tileDep && (c.dep0.x != 0.0f || c.dep0.y != 0.0f)) dep[ci] = make_float2(0.f, 0.f);
     }
   }
-  if (tid == 0) {  // consumed (no other CTA of this launch looks at this tile's flags)
-    if (tileFb) sg.dirtyFb[dirtyIdx] = 0;
-    if (tileDep) sg.dirtyDep[dirtyIdx] = 0;
-  }
+  if (tid == 0 && dirtyBits) sg.dirty[dirtyIdx] = 0;  // consumed (no other CTA of this launch looks at this tile's word)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,9 +12,10 @@
 //   k_precipitation  updates the droplets and adds each active droplet ONCE (one vector atomic,
 //                    red.global.add.v4.f32, + one v2 for the rare deposition) to its origin cell,
 //                    marking the <= 4 tiles its sprite touches in a dirty map;
-//   k_boxsum         for dirty 64 x 16 tiles only: origins of the tile + 11-cell apron -> shared
-//                    memory, 12-tap row sums, 12-tap column sums, added to feedback / deposition;
-//   k_clear_origins  zeroes the origin cells of dirty tiles;
+//   k_boxsum         for the dirty 64 x 16 tiles only (a persistent grid walks the list of tiles the
+//                    particle pass touched): origins of the tile + 11-cell apron -> shared memory,
+//                    12-tap row sums, 12-tap column sums, added to feedback / deposition;
+//   k_clear_origins  zeroes the origin cells of the listed tiles and resets the list;
 // and k_fused_pvb reads (and clears) feedback / deposition in dirty tiles only.  Overlapping
 // sprites therefore sum in an order of their own — equal to the reference's up to fp32 rounding.
 // 1-pixel sprites (spawn marker, lightning bolt, inactive count) are added to the target directly.
@@ -187,6 +188,12 @@ constexpr int kSpriteSize = 12;             // pntSize of precipitationShader.ve
 constexpr int kOriginShift = kSpriteSize / 2;  // origin cell = first covered pixel + 6, in [0, W] x [0, H]
 constexpr int kPTX = kTX, kPTY = kTY;       // dirty-map tiles = the tiles of k_fused_pvb
 
+// first toucher of a tile appends it to the list
+__device__ __forceinline__ void mark_dirty(const SpriteGrid& sg, int tile, int bits) {
+  if ((sg.dirty[tile] & bits) == bits) return;  // already flagged (plain read: a stale 0 only costs the atomic below)
+  if (atomicOr(&sg.dirty[tile], bits) == 0) sg.dirtyList[atomicAdd(sg.dirtyCount, 1)] = tile;
+}
+
 // One thread per droplet.  Inactive droplets (the majority) only count themselves: the count is
 // reduced per block and lands on texel (0,0) with one atomic (sums of 1.0 are exact in fp32).
 __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__ dropsIn, float* __restrict__ dropsOut,
@@ -218,18 +225,12 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
         const int tx0 = max(xs, 0) / kPTX, tx1 = min(xs + kSpriteSize - 1, g.pitch - 1) / kPTX;
         const int ty0 = max(ys, 0) / kPTY, ty1 = min(ys + kSpriteSize - 1, g.H - 1) / kPTY;
         for (int ty = ty0; ty <= ty1; ty++)
-          for (int tx = tx0; tx <= tx1; tx++) {
-            sg.dirtyFb[ty * sg.tilesX + tx] = 1;
-            if (hasDep) sg.dirtyDep[ty * sg.tilesX + tx] = 1;
-          }
+          for (int tx = tx0; tx <= tx1; tx++) mark_dirty(sg, ty * sg.tilesX + tx, hasDep ? (kDirtyFb | kDirtyDep) : kDirtyFb);
       } else if (xs >= 0 && xs < g.pitch && ys >= 0 && ys < g.H) {  // 1-pixel sprite: spawn marker, lightning bolt
         const size_t ci = (size_t)ys * g.pitch + xs;
         atomicAdd(&fb[ci], r.feedback);
-        sg.dirtyFb[(ys / kPTY) * sg.tilesX + xs / kPTX] = 1;
-        if (hasDep) {
-          atomicAdd(&dep[ci], r.deposition);
-          sg.dirtyDep[(ys / kPTY) * sg.tilesX + xs / kPTX] = 1;
-        }
+        if (hasDep) atomicAdd(&dep[ci], r.deposition);
+        mark_dirty(sg, (ys / kPTY) * sg.tilesX + xs / kPTX, hasDep ? (kDirtyFb | kDirtyDep) : kDirtyFb);
       }
     }
   }
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
   __syncthreads();
   if (threadIdx.x == 0 && sInactive > 0) {
     atomicAdd(&fb[0], make_float4((float)sInactive, 0.0f, 0.0f, 0.0f));
-    sg.dirtyFb[0] = 1;
+    mark_dirty(sg, 0, kDirtyFb);
   }
 }
 
@@ -245,8 +246,13 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
 //   pixel (x, y) is covered by the sprites whose first pixel lies in [x - 11, x] x [y - 11, y], i.e. whose ORIGIN
 //   cell (first pixel + 6) lies in [x - 5, x + 6] x [y - 5, y + 6].
 constexpr int kBoxW = kPTX + kSpriteSize - 1, kBoxH = kPTY + kSpriteSize - 1;  // 75 x 27 origins per tile
-constexpr int kBoxPitch = kBoxW + 1;
-constexpr size_t kSmemBox = (size_t)(kBoxH * kBoxPitch + kBoxH * kPTX) * sizeof(float4);
+// The row pass gives every thread THREE adjacent outputs (14 inputs in registers): with 16-byte elements an odd
+// number per thread keeps the eight lanes of a quarter warp on different banks (four per thread put them on two:
+// ncu showed 2.7 wavefronts per ideal one, profiles/r3_particles_ncu_summary.txt).  64 is not a multiple of 3: the
+// pass computes 66 columns from 77 (two zero-padded) and the column pass ignores the last two.
+constexpr int kRowOut = (kPTX + 2) / 3 * 3;           // 66
+constexpr int kBoxPitch = kRowOut + kSpriteSize - 1;  // 77
+constexpr size_t kSmemBox = (size_t)(kBoxH * kBoxPitch + kBoxH * kRowOut) * sizeof(float4);
 __device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ bool vnonzero(float4 a) { return a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f; }
@@ -258,64 +264,97 @@ template <class V>
 __device__ __forceinline__ void boxsum_tile(const V* __restrict__ org, V* __restrict__ target, int Po, int W, int H, int pitch, int X0,
                                             int Y0, V* sOrg, V* sRow) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < kBoxH * kBoxW; i += blockDim.x) {
-    const int r = i / kBoxW, c = i - r * kBoxW;
+  for (int i = tid; i < kBoxH * kBoxPitch; i += blockDim.x) {
+    const int r = i / kBoxPitch, c = i - r * kBoxPitch;
     const int oj = Y0 - (kSpriteSize - 1 - kOriginShift) + r, oi = X0 - (kSpriteSize - 1 - kOriginShift) + c;
     V v;
     vzero(v);
-    if (oj >= 0 && oj <= H && oi >= 0 && oi <= W) v = org[(size_t)oj * Po + oi];
-    sOrg[r * kBoxPitch + c] = v;
+    if (c < kBoxW && oj >= 0 && oj <= H && oi >= 0 && oi <= W) v = org[(size_t)oj * Po + oi];
+    sOrg[i] = v;
   }
   __syncthreads();
-  for (int i = tid; i < kBoxH * kPTX; i += blockDim.x) {  // 12-tap row sums
-    const int r = i / kPTX, c = i - r * kPTX;
-    V a = sOrg[r * kBoxPitch + c];
+  // 12-tap sums with the inputs every window of a thread shares summed once: rows, three adjacent outputs per thread
+  // (14 inputs: 15 vector adds, 14 shared-memory loads for 3 outputs instead of 33 and 36) ...
+  static_assert(kSpriteSize == 12 && kPTY % 4 == 0, "window sharing below is written for 12 taps");
+  for (int i = tid; i < kBoxH * (kRowOut / 3); i += blockDim.x) {
+    const int r = i / (kRowOut / 3), c = (i - r * (kRowOut / 3)) * 3;
+    const V* p = sOrg + r * kBoxPitch + c;
+    V in[14];
 #pragma unroll
-    for (int k = 1; k < kSpriteSize; k++) a = vadd(a, sOrg[r * kBoxPitch + c + k]);
-    sRow[i] = a;
+    for (int k = 0; k < 14; k++) in[k] = p[k];
+    V core = in[2];
+#pragma unroll
+    for (int k = 3; k < 12; k++) core = vadd(core, in[k]);
+    V* o = sRow + r * kRowOut + c;
+    o[0] = vadd(vadd(in[0], in[1]), core);
+    o[1] = vadd(vadd(in[1], core), in[12]);
+    o[2] = vadd(core, vadd(in[12], in[13]));
   }
   __syncthreads();
-  for (int i = tid; i < kPTY * kPTX; i += blockDim.x) {  // 12-tap column sums
-    const int ty = i / kPTX, tx = i - ty * kPTX;
-    V a = sRow[ty * kPTX + tx];
+  // ... columns, four adjacent outputs per thread (15 inputs, consecutive lanes on consecutive columns)
+  for (int i = tid; i < (kPTY / 4) * kPTX; i += blockDim.x) {  // column sums: (rows 4q .. 4q+3, column tx)
+    const int q = i / kPTX, tx = i - q * kPTX, ty = q * 4;
+    const V* p = sRow + ty * kRowOut + tx;
+    V in[15];
 #pragma unroll
-    for (int k = 1; k < kSpriteSize; k++) a = vadd(a, sRow[(ty + k) * kPTX + tx]);
-    const int x = X0 + tx, y = Y0 + ty;
-    if (x < W && y < H && vnonzero(a)) {
-      const size_t ci = (size_t)y * pitch + x;
-      target[ci] = vadd(target[ci], a);  // texels hit by 1-pixel sprites already hold their value
+    for (int k = 0; k < 15; k++) in[k] = p[k * kRowOut];
+    V core = in[3];
+#pragma unroll
+    for (int k = 4; k < 12; k++) core = vadd(core, in[k]);
+    V out[4];
+    out[0] = vadd(vadd(in[0], in[1]), vadd(in[2], core));
+    out[1] = vadd(vadd(in[1], in[2]), vadd(core, in[12]));
+    out[2] = vadd(vadd(in[2], core), vadd(in[12], in[13]));
+    out[3] = vadd(vadd(core, in[12]), vadd(in[13], in[14]));
+    const int x = X0 + tx;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int y = Y0 + ty + k;
+      if (x < W && y < H && vnonzero(out[k])) {
+        const size_t ci = (size_t)y * pitch + x;
+        target[ci] = vadd(target[ci], out[k]);  // texels hit by 1-pixel sprites already hold their value
+      }
     }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_boxsum(SpriteGrid sg, float4* __restrict__ fb, float2* __restrict__ dep, int W, int H, int pitch) {
-  const int tile = blockIdx.y * sg.tilesX + blockIdx.x;
-  const bool doFb = sg.dirtyFb[tile] != 0, doDep = sg.dirtyDep[tile] != 0;
-  if (!doFb && !doDep) return;
+// Persistent grid (a few CTAs per SM): CTA b takes list entries b, b + gridDim.x, ...
+__global__ void __launch_bounds__(256, 3) k_boxsum(SpriteGrid sg, float4* __restrict__ fb, float2* __restrict__ dep, int W, int H, int pitch) {
   WSB_DYN_SMEM(smem_raw);
   float4* sOrg = reinterpret_cast<float4*>(smem_raw);
   float4* sRow = sOrg + kBoxH * kBoxPitch;
-  const int X0 = blockIdx.x * kPTX, Y0 = blockIdx.y * kPTY;
-  if (doFb) boxsum_tile<float4>(sg.org4, fb, sg.Po, W, H, pitch, X0, Y0, sOrg, sRow);
-  if (doDep) boxsum_tile<float2>(sg.org2, dep, sg.Po, W, H, pitch, X0, Y0, reinterpret_cast<float2*>(sOrg), reinterpret_cast<float2*>(sRow));
+  const int n = *sg.dirtyCount;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int tile = sg.dirtyList[i], bits = sg.dirty[tile];
+    const int X0 = (tile % sg.tilesX) * kPTX, Y0 = (tile / sg.tilesX) * kPTY;
+    if (bits & kDirtyFb) boxsum_tile<float4>(sg.org4, fb, sg.Po, W, H, pitch, X0, Y0, sOrg, sRow);
+    if (bits & kDirtyDep) boxsum_tile<float2>(sg.org2, dep, sg.Po, W, H, pitch, X0, Y0, reinterpret_cast<float2*>(sOrg), reinterpret_cast<float2*>(sRow));
+  }
 }
 
-// Every non-zero origin cell lies inside its own sprite, i.e. inside a dirty tile (or in the extra column W / row H,
-// which the last tile column / row owns): zero the origin cells of dirty tiles.  A kernel of its own because the
-// box sums of neighbouring tiles read each other's origins.
-__global__ void __launch_bounds__(256) k_clear_origins(SpriteGrid sg, int W, int H) {
-  const int tile = blockIdx.y * sg.tilesX + blockIdx.x;
-  const bool doFb = sg.dirtyFb[tile] != 0, doDep = sg.dirtyDep[tile] != 0;
-  if (!doFb && !doDep) return;
-  const int X0 = blockIdx.x * kPTX, Y0 = blockIdx.y * kPTY;
-  const int X1 = (blockIdx.x == (unsigned)sg.tilesX - 1) ? W + 1 : X0 + kPTX, Y1 = (blockIdx.y == (unsigned)sg.tilesY - 1) ? H + 1 : Y0 + kPTY;
-  const int w = X1 - X0, n = w * (Y1 - Y0);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = i / w, c = i - r * w;
-    const size_t oi = (size_t)(Y0 + r) * sg.Po + X0 + c;
-    if (doFb) sg.org4[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (doDep) sg.org2[oi] = make_float2(0.f, 0.f);
+// Every non-zero origin cell lies inside its own sprite, i.e. inside a listed tile (or in the extra column W / row H,
+// which the last tile column / row owns): zero the origin cells of the listed tiles.  A kernel of its own because the
+// box sums of neighbouring tiles read each other's origins.  The last CTA to finish resets the list.
+__global__ void __launch_bounds__(256) k_clear_origins(SpriteGrid sg, int W, int H, unsigned* __restrict__ ctasDone) {
+  const int n = *sg.dirtyCount;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int tile = sg.dirtyList[i], bits = sg.dirty[tile];
+    const int bx = tile % sg.tilesX, by = tile / sg.tilesX;
+    const int X0 = bx * kPTX, Y0 = by * kPTY;
+    const int X1 = (bx == sg.tilesX - 1) ? W + 1 : X0 + kPTX, Y1 = (by == sg.tilesY - 1) ? H + 1 : Y0 + kPTY;
+    const int w = X1 - X0, cells = w * (Y1 - Y0);
+    for (int k = threadIdx.x; k < cells; k += blockDim.x) {
+      const int r = k / w, c = k - r * w;
+      const size_t oi = (size_t)(Y0 + r) * sg.Po + X0 + c;
+      if (bits & kDirtyFb) sg.org4[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bits & kDirtyDep) sg.org2[oi] = make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();  // every thread of this CTA has read the count
+  if (threadIdx.x == 0 && atomicAdd(ctasDone, 1u) == gridDim.x - 1) {
+    *ctasDone = 0u;
+    *sg.dirtyCount = 0;
   }
 }
 

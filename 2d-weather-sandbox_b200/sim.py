@@ -36,7 +36,7 @@ VIEW_FRAMEBUFF_0, VIEW_FRAMEBUFF_1, VIEW_LATEST = range(3)
 SCHEDULE_FUSED, SCHEDULE_REFERENCE = 0, 1
 (PASS_VELOCITY, PASS_CURL, PASS_VORTICITY, PASS_BOUNDARY, PASS_ADVECTION, PASS_PRESSURE, PASS_LIGHTING,
  PASS_PRECIPITATION, PASS_ITER_INC, PASS_ADVECTION_DRY) = range(10)
-KERNEL_PVB, KERNEL_ADV, KERNEL_DRY, KERNEL_PRECIP, KERNEL_HALO, KERNEL_WAIT, KERNEL_EDGE = range(7)
+KERNEL_PVB, KERNEL_ADV, KERNEL_DRY, KERNEL_PRECIP, KERNEL_HALO, KERNEL_WAIT, KERNEL_EDGE, KERNEL_SPRITES = range(8)
 COMM_ID_BYTES = 128
 PEER_INFO_BYTES = 256
 ABI_VERSION = 1

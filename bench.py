@@ -353,11 +353,23 @@ def run_ours(args):
     sus_sampler = ClockSampler(local_rank)
     _barrier(world)
     sus_sampler.start()
-    batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES, world, device)
+    batches = _timed_batches(sim, sim.step, K, 3 if args.quick else SUSTAINED_BATCHES, world, device)
     sus_clocks = sus_sampler.result()
     med = float(np.median(batches))
     sustained = {"batches": len(batches), "steps_per_batch": K, "ms_per_step_median": med, "ms_per_step_min": min(batches), "ms_per_step_max": max(batches),
                  "value_median": W * H / (med * 1e-3), "unit": UNIT, "clocks": sus_clocks}
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms / K, "sustained": sustained, "per_rank": roofline.get("per_rank"),
+                              "kernels_ms_per_step": roofline["kernels_ms_per_step"]}), flush=True)
+        sim.close()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the public API ------------
     ob, ow, ol = _pinned((H, lw, 4), np.float32), _pinned((H, lw, 4), np.float32), _pinned((H, lw, 4), np.int8)
@@ -553,7 +565,8 @@ def particles_leg(W, H, K, Wm, peak, peak_src, device_index, nd):
     sim.sync()
     clocks = sampler.result()
     ms = sim.last_step_ms()
-    kt = {n: sim.kernel_time_ms(k) for n, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("k_precipitation", S.KERNEL_PRECIP))}
+    kt = {n: sim.kernel_time_ms(k) for n, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV), ("particle_pass", S.KERNEL_PRECIP),
+                                                ("of_which_boxsum_and_clear", S.KERNEL_SPRITES))}
     d = sim.read_droplets()
     dom = max(("k_fused_pvb", "k_fused_adv"), key=lambda n: kt[n][0])
     rl = _roofline(dom, kt[dom][0] / max(kt[dom][1], 1), W * H, peak, peak_src, W, H, 1)
@@ -580,6 +593,7 @@ def main():
     ap.add_argument("--height", type=int, default=GRID_H)
     ap.add_argument("--headline-only", action="store_true", help="N=1: skip the extra legs (dry sweep, configs 2-4, cpu baseline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="experiments: headline batch + 3 sustained batches only (no e2e, no 1-GPU comparison)")
     ap.add_argument("--no-prewarm", action="store_true", help="skip the clock ramp-up iterations (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -269,12 +269,13 @@ enum {
   WSB_KERNEL_PVB = 0,    /* k_fused_pvb: pressure -> velocity -> curl -> vorticity -> boundary */
   WSB_KERNEL_ADV = 1,    /* k_fused_adv: advection -> lighting */
   WSB_KERNEL_DRY = 2,    /* k_fused_dry: velocity -> advection(base) -> pressure */
-  WSB_KERNEL_PRECIP = 3, /* k_precipitation + k_latch */
+  WSB_KERNEL_PRECIP = 3, /* the whole particle pass: k_precipitation + k_boxsum + k_clear_origins + k_latch */
   WSB_KERNEL_HALO = 4,   /* ghost exchange on the communication stream: k_push_ghosts (peer transport) or
                             pack + ncclSend/Recv + unpack (NCCL transport) */
   WSB_KERNEL_WAIT = 5,   /* k_wait_ghosts: time spent waiting for the neighbours' columns */
-  WSB_KERNEL_EDGE = 6    /* strips, peer transport: the edge tile columns of k_fused_pvb / k_fused_adv, which run on the
+  WSB_KERNEL_EDGE = 6,   /* strips, peer transport: the edge tile columns of k_fused_pvb / k_fused_adv, which run on the
                             communication stream beside the interior tile columns (PVB / ADV then time the interior only) */
+  WSB_KERNEL_SPRITES = 7 /* k_boxsum + k_clear_origins (part of PRECIP): the sprites as a box filter over the dirty tiles */
 };
 int wsb_set_profiling(wsb_sim* sim, int32_t on);
 int wsb_kernel_time_ms(wsb_sim* sim, int32_t kernel, float* total_ms, int32_t* launches);

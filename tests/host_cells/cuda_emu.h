@@ -117,6 +117,18 @@ inline void launch(dim3 grid, int nthreads, size_t smem_bytes, const std::functi
 #define gridDim (emu::tls.gdim)
 
 static inline void __syncthreads() { emu::tls.cta->bar.arrive_and_wait(); }
+// block-wide OR: the warp slots of warp 0 double as the CTA's scratch word
+namespace emu { inline std::atomic<int> cta_or{0}; }
+static inline int __syncthreads_or(int pred) {
+  emu::tls.cta->bar.arrive_and_wait();
+  if (emu::tls.tid.x == 0) emu::cta_or.store(0);
+  emu::tls.cta->bar.arrive_and_wait();
+  if (pred) emu::cta_or.store(1);
+  emu::tls.cta->bar.arrive_and_wait();
+  const int r = emu::cta_or.load();
+  emu::tls.cta->bar.arrive_and_wait();
+  return r;
+}
 static inline unsigned __activemask() { return 0xffffffffu; }
 static inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
@@ -141,6 +153,8 @@ template <class F> static inline void emu_locked(F&& f) {
 }
 static inline void atomicAdd(float4* p, float4 v) { emu_locked([&] { p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; }); }
 static inline void atomicAdd(float2* p, float2 v) { emu_locked([&] { p->x += v.x; p->y += v.y; }); }
+static inline int atomicOr(int* p, int v) { int old = 0; emu_locked([&] { old = *p; *p |= v; }); return old; }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned old = 0; emu_locked([&] { old = *p; *p += v; }); return old; }
 static inline int atomicAdd(int* p, int v) { int old = 0; emu_locked([&] { old = *p; *p += v; }); return old; }
 // full-warp collectives (the kernels only call them with every lane of the warp present)
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {

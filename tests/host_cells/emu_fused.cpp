@@ -36,8 +36,11 @@ struct Sim {
   // sprite origins + dirty-tile map of the particle pass (csrc/wsb200.cu: alloc_all)
   std::vector<float4> org4;
   std::vector<float2> org2;
-  std::vector<unsigned char> dirtyFb, dirtyDep;
+  std::vector<int> dirty, dirtyList;
+  int dirtyCount[2] = {0, 0};
   SpriteGrid sg{};
+  std::vector<unsigned char> tilewalls;  // k_fused_dry's tile map
+  bool tilewalls_valid = false;
   std::vector<float> initial_T, sndT, sndW, sndV;
   unsigned maxv = 0;
   std::vector<float> drops[2];
@@ -70,6 +73,7 @@ dim3 tile_grid(const Sim& s, int ty) { return dim3((s.W + kTX - 1) / kTX, (s.H +
 
 // csrc/wsb200.cu: fused_iteration, single domain, no particles
 void fused_iteration(Sim& s) {
+  s.tilewalls_valid = false;
   derived(s);
   const int src = s.even ? 0 : 1, dst = s.even ? 1 : 0;
   {
@@ -83,7 +87,7 @@ void fused_iteration(Sim& s) {
     maps.m[9] = map_of(s, s.light[0].p.c[0], kTX, kTY);
     maps.m[10] = map_of(s, s.light[0].p.c[1], kTX, kTY);
     const DevParams d = s.dp;
-    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = (s.fb_dirty && s.sg.dirtyFb) ? 1 : 0;
+    const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0, useFb = (s.fb_dirty && s.sg.dirty) ? 1 : 0;
     auto launch_pvb = [&](int cx0, int cx1, int gapAt, int gapLen) {
       c.g.cx0 = cx0; c.g.cx1 = cx1; c.g.cxGapAt = gapAt; c.g.cxGapLen = gapLen;
       emu::launch(dim3((cx1 - cx0 - gapLen + kTX - 1) / kTX, (s.H + kTY - 1) / kTY), kNT, kSmem1, [&] {
@@ -145,9 +149,9 @@ void fused_iteration(Sim& s) {
       k_precipitation(s.drops[psrc].data(), s.drops[pdst].data(), s.base[1].p, s.water[1].p, s.fb.data(), s.dep.data(), s.sg, s.lightning,
                       &s.inactive, s.g, d, s.ND);
     });
-    const dim3 tiles(s.sg.tilesX, s.sg.tilesY);
-    emu::launch(tiles, 256, kSmemBox, [&] { k_boxsum(s.sg, s.fb.data(), s.dep.data(), s.W, s.H, s.W); });
-    emu::launch(tiles, 256, 0, [&] { k_clear_origins(s.sg, s.W, s.H); });
+    const dim3 ctas(std::min(5, s.sg.tilesX * s.sg.tilesY), 1);  // persistent grid walking the dirty-tile list
+    emu::launch(ctas, 256, kSmemBox, [&] { k_boxsum(s.sg, s.fb.data(), s.dep.data(), s.W, s.H, s.W); });
+    emu::launch(ctas, 256, 0, [&] { k_clear_origins(s.sg, s.W, s.H, reinterpret_cast<unsigned*>(&s.dirtyCount[1])); });
     s.fb_dirty = true;
     s.last_drops = pdst;
     emu::launch(dim3(1, 1), 32, 0, [&] { k_latch(s.fb.data(), &s.inactive, s.lightning, d.iterNum, (s.iter % 600 == 0) ? 1 : 0); });
@@ -164,7 +168,14 @@ void dry_iteration(Sim& s) {
   maps.m[4] = map_of(s, s.wall[1].data(), kSWD, kSHD);
   const DevParams d = s.dp;
   const int useTma = s.use_tma, applyPressure = s.pressure_pending ? 1 : 0;
-  emu::launch(tile_grid(s, kTYD), kNT, kSmemDry, [&] { k_fused_dry(c, d, maps, useTma, applyPressure, s.base[0].p, &s.maxv); });
+  const dim3 tiles = tile_grid(s, kTYD);
+  if (!s.tilewalls_valid) {  // csrc/wsb200.cu: dry_iteration — the wall texture may have changed since the last dry sweep
+    s.tilewalls.assign((size_t)tiles.x * tiles.y, 0xCD);
+    emu::launch(tiles, 256, 0, [&] { k_wall_tilemap(c, s.tilewalls.data()); });
+    s.tilewalls_valid = true;
+    s.launches++;
+  }
+  emu::launch(tiles, kNT, kSmemDry, [&] { k_fused_dry(c, d, maps, useTma, applyPressure, s.tilewalls.data(), s.base[0].p, &s.maxv); });
   s.launches++;
   std::swap(s.base[0], s.base[1]);
   s.pressure_pending = true;
@@ -208,7 +219,7 @@ void ef_upload(void* h, const float* base, const float* water, const int8_t* wal
       for (int ch = 0; ch < 4; ch++) { s.base[k].data[ch][i] = base[i * 4 + ch]; s.water[k].data[ch][i] = water[i * 4 + ch]; s.light[k].data[ch][i] = 0.0f; }
       int w; memcpy(&w, wall + i * 4, 4); s.wall[k][i] = w;
     }
-  s.even = true; s.iter = 0; s.pressure_pending = false; s.maxv = 0;
+  s.even = true; s.iter = 0; s.pressure_pending = false; s.maxv = 0; s.tilewalls_valid = false;
   derived(s);
 }
 void ef_upload_drops(void* h, const float* drops, int nd) {
@@ -226,9 +237,10 @@ void ef_upload_drops(void* h, const float* drops, int nd) {
   sg.tilesY = (s.H + kPTY - 1) / kPTY;
   s.org4.assign((size_t)sg.Po * (s.H + 1), make_float4(0.f, 0.f, 0.f, 0.f));
   s.org2.assign((size_t)sg.Po * (s.H + 1), make_float2(0.f, 0.f));
-  s.dirtyFb.assign((size_t)sg.tilesX * sg.tilesY, 0);
-  s.dirtyDep.assign((size_t)sg.tilesX * sg.tilesY, 0);
-  sg.org4 = s.org4.data(); sg.org2 = s.org2.data(); sg.dirtyFb = s.dirtyFb.data(); sg.dirtyDep = s.dirtyDep.data();
+  s.dirty.assign((size_t)sg.tilesX * sg.tilesY, 0);
+  s.dirtyList.assign((size_t)sg.tilesX * sg.tilesY, -1);
+  s.dirtyCount[0] = s.dirtyCount[1] = 0;
+  sg.org4 = s.org4.data(); sg.org2 = s.org2.data(); sg.dirty = s.dirty.data(); sg.dirtyList = s.dirtyList.data(); sg.dirtyCount = s.dirtyCount;
 }
 // non-zero sprite-origin cells left after a step (k_clear_origins must leave none), and dirty tiles still flagged
 int ef_origin_residue(void* h, int* dirty_tiles) {
@@ -236,7 +248,8 @@ int ef_origin_residue(void* h, int* dirty_tiles) {
   int n = 0, d = 0;
   for (const float4& v : s.org4) n += (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f);
   for (const float2& v : s.org2) n += (v.x != 0.f || v.y != 0.f);
-  for (size_t i = 0; i < s.dirtyFb.size(); i++) d += (s.dirtyFb[i] != 0) || (s.dirtyDep[i] != 0);
+  for (size_t i = 0; i < s.dirty.size(); i++) d += s.dirty[i] != 0;
+  if (s.dirtyCount[0] != 0 || s.dirtyCount[1] != 0) n += 1000000;  // the list must have been reset
   *dirty_tiles = d;
   return n;
 }
