@@ -584,7 +584,7 @@ int precipitation(wsb_sim* s) {
   LAUNCHED("k_precipitation");
   {  // sprites = 12 x 12 box filter of the origins, on the tiles that were touched
     ProfScope profSprites(s, WSB_KERNEL_SPRITES);
-    const int ctas = std::min(s->n_sms * 3, s->sg.tilesX * s->sg.tilesY);  // persistent: the list of touched tiles is walked on the device
+    const int ctas = std::min(s->n_sms * 4, s->sg.tilesX * s->sg.tilesY);  // persistent: the list of touched tiles is walked on the device
     k_boxsum<<<ctas, 256, kSmemBox, s->stream>>>(s->sg, s->fb, s->dep, s->W, s->H, s->pitch);
     LAUNCHED("k_boxsum");
     k_clear_origins<<<ctas, 256, 0, s->stream>>>(s->sg, s->W, s->H, reinterpret_cast<unsigned*>(s->sg.dirtyCount + 1));

@@ -368,81 +368,26 @@ constexpr size_t kSmemDry = (size_t)kPSD * 4 * 6 + 16;
 #define WSB_DRY_CTAS 4   // resident CTAs per SM the register allocation is bounded for
 #endif
 
-// glob: base = base_1 (advection output, pressure pending), wall = wall_1.
-// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
-// (Tried and dropped, profiles/r2_dry_variants.md: results leaving through shared-memory tiles and
-// TMA box stores — the elected thread's wait for the store to drain keeps the CTA's slot busy, 4 %
-// slower than plain coalesced stores; a persistent grid with double-buffered TMA prefetch of the
-// next tile — hides the load latency completely but fits only 3 CTAs per SM, 7 % slower: the
-// kernel is bound by shared-memory wavefronts and issue slots, not by exposed HBM latency.)
-__global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_constant__ GlobalCtx glob,
-                                                      const __grid_constant__ DevParams d,
-                                                      const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
-                                                      const unsigned char* __restrict__ tileWalls, Planes4 baseOut,
-                                                      unsigned* __restrict__ maxv) {
-  WSB_DYN_SMEM(smem_raw);
-  float* sVX = reinterpret_cast<float*>(smem_raw);
-  float* sVY = sVX + kPSD;
-  float* sP = sVY + kPSD;
-  float* sT = sP + kPSD;    // raw T
-  int* sWl = reinterpret_cast<int*>(sT + kPSD);
-  float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
-  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
-  unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
-  unsigned* sAnyWall = sMax + 1;                            // any wall cell in staged rows 1 .. SH-2
+// Advection of the base field on one tile (the third stage of k_fused_dry).  WALLS = false: no wall cell anywhere
+// in the staged region — the own cell's wall test and the wall-aware bilerp weights fall away at compile time, and T
+// after the pressure pass IS the staged T (plane 3 instead of plane 5).
+template <bool WALLS>
+__device__ __forceinline__ float dry_advect_tile(const GlobalCtx& glob, const DevParams& d, int applyPressure, const float* sVX,
+                                                 int X0, int Y0, Planes4 baseOut) {
   constexpr int SW = kSWD;
-
+  constexpr bool walls = WALLS;
   const Geom& g = glob.g;
   const int tid = threadIdx.x;
-  const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTYD - kHD;
-
-  // tileWalls[tile] == 0: no wall cell anywhere in this tile's staged region (k_wall_tilemap; the dry sweep never
-  // changes the wall texture, so the map stays valid between wall-changing calls).  Such tiles — all of the free
-  // atmosphere — do not stage the wall plane at all (16 of 20 staged bytes per cell, 32 of 36 B / cell of HBM traffic),
-  // their sweeps skip the wall tests and the land-wall rule of the pressure pass (T' == T).
-  const bool walls = tileWalls == nullptr || tileWalls[blockIdx.y * gridDim.x + blockIdx.x] != 0;
-  if (tid == 0) { *sMax = 0u; *sAnyWall = 0u; }
-  if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    if (tid == 0) {
-      mbar_expect_tx(mbar, (walls ? 5u : 4u) * kND * 4u);
-      tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
-      tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
-      tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
-      tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
-      if (walls) tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
-    }
-    mbar_wait(mbar, 0);
-  } else {
-    stage_tile<kSWD, kSHD, 6>(
-        g, X0, Y0,
-        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], walls ? glob.wall[ci] : 0x0100}; },
-        [&](int s, const BaseWallRegs& r) {
-          sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
-          sWl[s] = r.w;
-        });
-    __syncthreads();
-  }
-
-  if (walls) {
-    sweep_pressure<kSWD, kND, true>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
-    __syncthreads();
-    sweep_velocity<kSWD, kND, true>(d, sVX, sVY, sP, sWl);
-  } else {
-    sweep_pressure<kSWD, kND, false>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
-    __syncthreads();
-    sweep_velocity<kSWD, kND, false>(d, sVX, sVY, sP, sWl);
-  }
-  __syncthreads();
+  const float* sVY = sVX + kPSD;
+  const float* sP = sVY + kPSD;
+  const int* sWl = reinterpret_cast<const int*>(sVX + 4 * kPSD);
+  const float* sT2 = sVX + 5 * kPSD;
+  (void)sP; (void)sWl; (void)sT2;
 #if WSB_OPT_NEAR
-  const int tPlane = walls ? 5 * kPSD : 3 * kPSD;   // T after the pressure pass, as a displacement from the VX plane
+  constexpr int tPlane = WALLS ? 5 * kPSD : 3 * kPSD;   // T after the pressure pass, as a displacement from the VX plane
 #else
-  const float* sTpost = walls ? sT2 : sT;
+  const float* sTpost = WALLS ? sT2 : sVX + 3 * kPSD;
 #endif
-
-  // advection of the base field on the tile.  On an all-air tile the own cell's wall test and the wall-aware
-  // bilerp weights fall away: every tap of a near back-trace lies in the staged region.
   float vm = 0.0f;
   const int tx = tid % kTX, ty0 = tid / kTX;
   const int x = X0 + kHX + tx;
@@ -518,6 +463,76 @@ __global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_co
     }
   }
   if (x < g.ox0 || x >= g.ox1) vm = 0.0f;  // ghost columns hold the neighbour's cells (and edge garbage)
+  return vm;
+}
+
+// glob: base = base_1 (advection output, pressure pending), wall = wall_1.
+// maps: TMA descriptors of glob.base.c[0..3] and glob.wall with a kSWD x kSHD box.
+// (Tried and dropped, profiles/r2_dry_variants.md: results leaving through shared-memory tiles and
+// TMA box stores — the elected thread's wait for the store to drain keeps the CTA's slot busy, 4 %
+// slower than plain coalesced stores; a persistent grid with double-buffered TMA prefetch of the
+// next tile — hides the load latency completely but fits only 3 CTAs per SM, 7 % slower: the
+// kernel is bound by shared-memory wavefronts and issue slots, not by exposed HBM latency.)
+__global__ void __launch_bounds__(kNT, WSB_DRY_CTAS) k_fused_dry(const __grid_constant__ GlobalCtx glob,
+                                                      const __grid_constant__ DevParams d,
+                                                      const __grid_constant__ TileMaps<5> maps, int useTma, int applyPressure,
+                                                      const unsigned char* __restrict__ tileWalls, Planes4 baseOut,
+                                                      unsigned* __restrict__ maxv) {
+  WSB_DYN_SMEM(smem_raw);
+  float* sVX = reinterpret_cast<float*>(smem_raw);
+  float* sVY = sVX + kPSD;
+  float* sP = sVY + kPSD;
+  float* sT = sP + kPSD;    // raw T
+  int* sWl = reinterpret_cast<int*>(sT + kPSD);
+  float* sT2 = reinterpret_cast<float*>(sWl + kPSD);   // T after the pressure pass
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sT2 + kPSD);
+  unsigned* sMax = reinterpret_cast<unsigned*>(mbar + 1);  // CTA maximum of |v| (report_vmax_cta)
+
+  const Geom& g = glob.g;
+  const int tid = threadIdx.x;
+  const int X0 = tile_col0(g, blockIdx.x, kTX) - kHX, Y0 = blockIdx.y * kTYD - kHD;
+
+  // tileWalls[tile] == 0: no wall cell anywhere in this tile's staged region (k_wall_tilemap; the dry sweep never
+  // changes the wall texture, so the map stays valid between wall-changing calls).  Such tiles — all of the free
+  // atmosphere — do not stage the wall plane at all (16 of 20 staged bytes per cell, 32 of 36 B / cell of HBM traffic),
+  // their sweeps skip the wall tests and the land-wall rule of the pressure pass (T' == T).
+  const bool walls = tileWalls == nullptr || tileWalls[blockIdx.y * gridDim.x + blockIdx.x] != 0;
+  if (tid == 0) *sMax = 0u;
+  if (tile_tma_ok<kSWD, kSHD>(g, useTma, X0, Y0)) {
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(mbar, (walls ? 5u : 4u) * kND * 4u);
+      tma_load_box(sVX, &maps.m[0], X0, Y0, mbar);
+      tma_load_box(sVY, &maps.m[1], X0, Y0, mbar);
+      tma_load_box(sP, &maps.m[2], X0, Y0, mbar);
+      tma_load_box(sT, &maps.m[3], X0, Y0, mbar);
+      if (walls) tma_load_box(sWl, &maps.m[4], X0, Y0, mbar);
+    }
+    mbar_wait(mbar, 0);
+  } else {
+    stage_tile<kSWD, kSHD, 6>(
+        g, X0, Y0,
+        [&](int ci, int) { return BaseWallRegs{glob.base.c[0][ci], glob.base.c[1][ci], glob.base.c[2][ci], glob.base.c[3][ci], walls ? glob.wall[ci] : 0x0100}; },
+        [&](int s, const BaseWallRegs& r) {
+          sVX[s] = r.vx; sVY[s] = r.vy; sP[s] = r.p; sT[s] = r.t;
+          sWl[s] = r.w;
+        });
+    __syncthreads();
+  }
+
+  if (walls) {
+    sweep_pressure<kSWD, kND, true>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
+    __syncthreads();
+    sweep_velocity<kSWD, kND, true>(d, sVX, sVY, sP, sWl);
+  } else {
+    sweep_pressure<kSWD, kND, false>(sVX, sVY, sP, sT, sT2, sWl, applyPressure);
+    __syncthreads();
+    sweep_velocity<kSWD, kND, false>(d, sVX, sVY, sP, sWl);
+  }
+  __syncthreads();
+  const float vm = walls ? dry_advect_tile<true>(glob, d, applyPressure, sVX, X0, Y0, baseOut)
+                         : dry_advect_tile<false>(glob, d, applyPressure, sVX, X0, Y0, baseOut);
   report_vmax_cta(vm, maxv, sMax);
 }
 

@@ -246,13 +246,16 @@ __global__ void __launch_bounds__(256) k_precipitation(const float* __restrict__
 //   pixel (x, y) is covered by the sprites whose first pixel lies in [x - 11, x] x [y - 11, y], i.e. whose ORIGIN
 //   cell (first pixel + 6) lies in [x - 5, x + 6] x [y - 5, y + 6].
 constexpr int kBoxW = kPTX + kSpriteSize - 1, kBoxH = kPTY + kSpriteSize - 1;  // 75 x 27 origins per tile
-// The row pass gives every thread THREE adjacent outputs (14 inputs in registers): with 16-byte elements an odd
-// number per thread keeps the eight lanes of a quarter warp on different banks (four per thread put them on two:
-// ncu showed 2.7 wavefronts per ideal one, profiles/r3_particles_ncu_summary.txt).  64 is not a multiple of 3: the
-// pass computes 66 columns from 77 (two zero-padded) and the column pass ignores the last two.
+// Column sums first (27 -> 16 rows, every staged column), then row sums straight into the target: 660 work items per
+// tile instead of 850 the other way round, and the intermediate is 16 rows instead of 27 (52.9 KB: 4 CTAs per SM).
+// Window sharing: a thread computes 4 vertically (3 horizontally) adjacent outputs from 15 (14) inputs held in
+// registers, summing the inputs all of its windows share once.  THREE per thread in the row pass because with 16-byte
+// elements an odd count keeps the eight lanes of a quarter warp on different banks (four per thread put them on two:
+// ncu showed 2.7 wavefronts per ideal one, profiles/r3_particles_ncu_summary.txt); 64 is not a multiple of 3, so the
+// staged region is padded to 77 columns (two of zeros) and the last two of 66 row outputs are dropped.
 constexpr int kRowOut = (kPTX + 2) / 3 * 3;           // 66
 constexpr int kBoxPitch = kRowOut + kSpriteSize - 1;  // 77
-constexpr size_t kSmemBox = (size_t)(kBoxH * kBoxPitch + kBoxH * kRowOut) * sizeof(float4);
+constexpr size_t kSmemBox = (size_t)(kBoxH * kBoxPitch + kPTY * kBoxPitch) * sizeof(float4);
 __device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float2 vadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ bool vnonzero(float4 a) { return a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f; }
@@ -262,7 +265,8 @@ __device__ __forceinline__ void vzero(float2& a) { a = make_float2(0.f, 0.f); }
 
 template <class V>
 __device__ __forceinline__ void boxsum_tile(const V* __restrict__ org, V* __restrict__ target, int Po, int W, int H, int pitch, int X0,
-                                            int Y0, V* sOrg, V* sRow) {
+                                            int Y0, V* sOrg, V* sCol) {
+  static_assert(kSpriteSize == 12 && kPTY % 4 == 0, "window sharing below is written for 12 taps");
   const int tid = threadIdx.x;
   for (int i = tid; i < kBoxH * kBoxPitch; i += blockDim.x) {
     const int r = i / kBoxPitch, c = i - r * kBoxPitch;
@@ -273,44 +277,40 @@ __device__ __forceinline__ void boxsum_tile(const V* __restrict__ org, V* __rest
     sOrg[i] = v;
   }
   __syncthreads();
-  // 12-tap sums with the inputs every window of a thread shares summed once: rows, three adjacent outputs per thread
-  // (14 inputs: 15 vector adds, 14 shared-memory loads for 3 outputs instead of 33 and 36) ...
-  static_assert(kSpriteSize == 12 && kPTY % 4 == 0, "window sharing below is written for 12 taps");
-  for (int i = tid; i < kBoxH * (kRowOut / 3); i += blockDim.x) {
+  for (int i = tid; i < (kPTY / 4) * kBoxPitch; i += blockDim.x) {  // column sums: (rows 4q .. 4q+3, staged column c)
+    const int q = i / kBoxPitch, c = i - q * kBoxPitch, ty = q * 4;
+    const V* p = sOrg + ty * kBoxPitch + c;
+    V in[15];
+#pragma unroll
+    for (int k = 0; k < 15; k++) in[k] = p[k * kBoxPitch];
+    V core = in[3];
+#pragma unroll
+    for (int k = 4; k < 12; k++) core = vadd(core, in[k]);
+    V* o = sCol + ty * kBoxPitch + c;
+    o[0] = vadd(vadd(in[0], in[1]), vadd(in[2], core));
+    o[kBoxPitch] = vadd(vadd(in[1], in[2]), vadd(core, in[12]));
+    o[2 * kBoxPitch] = vadd(vadd(in[2], core), vadd(in[12], in[13]));
+    o[3 * kBoxPitch] = vadd(vadd(core, in[12]), vadd(in[13], in[14]));
+  }
+  __syncthreads();
+  for (int i = tid; i < kPTY * (kRowOut / 3); i += blockDim.x) {  // row sums: (row r, columns 3t .. 3t+2) -> target
     const int r = i / (kRowOut / 3), c = (i - r * (kRowOut / 3)) * 3;
-    const V* p = sOrg + r * kBoxPitch + c;
+    const V* p = sCol + r * kBoxPitch + c;
     V in[14];
 #pragma unroll
     for (int k = 0; k < 14; k++) in[k] = p[k];
     V core = in[2];
 #pragma unroll
     for (int k = 3; k < 12; k++) core = vadd(core, in[k]);
-    V* o = sRow + r * kRowOut + c;
-    o[0] = vadd(vadd(in[0], in[1]), core);
-    o[1] = vadd(vadd(in[1], core), in[12]);
-    o[2] = vadd(core, vadd(in[12], in[13]));
-  }
-  __syncthreads();
-  // ... columns, four adjacent outputs per thread (15 inputs, consecutive lanes on consecutive columns)
-  for (int i = tid; i < (kPTY / 4) * kPTX; i += blockDim.x) {  // column sums: (rows 4q .. 4q+3, column tx)
-    const int q = i / kPTX, tx = i - q * kPTX, ty = q * 4;
-    const V* p = sRow + ty * kRowOut + tx;
-    V in[15];
+    V out[3];
+    out[0] = vadd(vadd(in[0], in[1]), core);
+    out[1] = vadd(vadd(in[1], core), in[12]);
+    out[2] = vadd(core, vadd(in[12], in[13]));
+    const int y = Y0 + r;
 #pragma unroll
-    for (int k = 0; k < 15; k++) in[k] = p[k * kRowOut];
-    V core = in[3];
-#pragma unroll
-    for (int k = 4; k < 12; k++) core = vadd(core, in[k]);
-    V out[4];
-    out[0] = vadd(vadd(in[0], in[1]), vadd(in[2], core));
-    out[1] = vadd(vadd(in[1], in[2]), vadd(core, in[12]));
-    out[2] = vadd(vadd(in[2], core), vadd(in[12], in[13]));
-    out[3] = vadd(vadd(core, in[12]), vadd(in[13], in[14]));
-    const int x = X0 + tx;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int y = Y0 + ty + k;
-      if (x < W && y < H && vnonzero(out[k])) {
+    for (int k = 0; k < 3; k++) {
+      const int x = X0 + c + k;
+      if (c + k < kPTX && x < W && y < H && vnonzero(out[k])) {
         const size_t ci = (size_t)y * pitch + x;
         target[ci] = vadd(target[ci], out[k]);  // texels hit by 1-pixel sprites already hold their value
       }
@@ -320,10 +320,10 @@ __device__ __forceinline__ void boxsum_tile(const V* __restrict__ org, V* __rest
 }
 
 // Persistent grid (a few CTAs per SM): CTA b takes list entries b, b + gridDim.x, ...
-__global__ void __launch_bounds__(256, 3) k_boxsum(SpriteGrid sg, float4* __restrict__ fb, float2* __restrict__ dep, int W, int H, int pitch) {
+__global__ void __launch_bounds__(256, 4) k_boxsum(SpriteGrid sg, float4* __restrict__ fb, float2* __restrict__ dep, int W, int H, int pitch) {
   WSB_DYN_SMEM(smem_raw);
   float4* sOrg = reinterpret_cast<float4*>(smem_raw);
-  float4* sRow = sOrg + kBoxH * kBoxPitch;
+  float4* sRow = sOrg + kBoxH * kBoxPitch;  // the column sums
   const int n = *sg.dirtyCount;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
     const int tile = sg.dirtyList[i], bits = sg.dirty[tile];

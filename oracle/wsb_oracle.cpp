@@ -5,16 +5,23 @@
 // libwsb200.so; nothing in the product may link, import or call it (only tests/, bench.py's
 // cpu_baseline / --impl reference leg and __graft_entry__.smoke()).
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or expected outputs for this path
-//  and its own implementation (GLSL ES 3.00 under a browser) cannot be executed
-// in this environment (no node / browser / GL / SwiftShader).  The oracle is therefore written
-// from the shader sources alone, one function per reference pass, each citing the file:line it
-// follows.  Where GLSL/WebGL leaves behaviour implementation-defined the canonical choice is
-// written next to the code (and listed in DESIGN.md "Spec freeze").  What pins it short of the
-// reference itself: every pass is reproduced bit for bit by a second, independent Python
-// restatement of its shader (tests/test_oracle_numpy_*.py, tests/test_oracle_python_*.py;
-// DESIGN.md 6 has the table), which catches transcription slips and disagreements between two
-// readings of the GLSL, not a shared misreading of what a WebGL implementation does.
+// PARITY: PINNED TO REFERENCE OUTPUT WHERE THE REFERENCE PRODUCED ANY; the fp32 trajectory itself is UNPINNED.
+// The reference ships no tests, golden vectors or expected outputs for this path and its own
+// implementation (GLSL ES 3.00 under a browser) cannot be executed in this environment (no node / browser / GL /
+// SwiftShader), so the oracle is written from the shader sources alone, one function per reference pass, each
+// citing the file:line it follows.  What the reference DID produce are its 14 shipped saves (frameBuff_0 read back
+// from the GPU, app.js:6575-6628).  tests/test_reference_saves.py holds the oracle to them: the integer wall planes
+// TYPE / DISTANCE / VERT_DISTANCE of every save are a fixed point of one more oracle iteration (0 changed bytes; only
+// LAND <-> FIRE flips in burning saves), the vegetation of every land surface cell is unchanged outside a growth tick
+// and the cells that do change are exactly the derived copies an older shader revision left stale, reference-written
+// invariants (wall marker, T == 1000, water-surface clamp, zero wall velocity) survive, and one iteration moves the
+// fp32 fields by the small fractions a running simulation moves (DESIGN.md 6 has the numbers).  NOT pinned: the fp32
+// values after N iterations of the WebGL path — nothing reference-produced exists to compare them with; there every
+// pass is reproduced bit for bit by a second, independent Python restatement of its shader
+// (tests/test_oracle_numpy_*.py, tests/test_oracle_python_*.py), which catches transcription slips and
+// disagreements between two readings of the GLSL, not a shared misreading of what a WebGL implementation does.
+// Where GLSL/WebGL leaves behaviour implementation-defined the canonical choice is written next to the code (and
+// listed in DESIGN.md "Spec freeze").
 //
 // Arithmetic is fp32 with no contraction (build with -ffp-contract=off) so that the CUDA kernels
 // (built with -fmad=false) can reproduce it operation for operation.
