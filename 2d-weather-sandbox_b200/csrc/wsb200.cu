@@ -209,7 +209,12 @@ __global__ void k_ghosts_free(const __grid_constant__ PushArgs a) {
 __global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ PushArgs a) {
   unsigned* myFlags = flag_of(a.mine, a.pbMine, 0);
   const int per = a.H * 2;  // (row, column quad)
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per * a.n; t += gridDim.x * blockDim.x) {
+  // every CTA takes a CONTIGUOUS run of (plane, row) items: consecutive rows of one plane share 2 MB pages, and the
+  // peer-memory stores of a CTA then touch ~20 pages instead of all 800 (a grid-stride loop made the push 5x slower)
+  const int total = per * a.n, chunk = (total + gridDim.x - 1) / gridDim.x;
+  const int tEnd = min(total, ((int)blockIdx.x + 1) * chunk);
+#pragma unroll 2
+  for (int t = blockIdx.x * chunk + threadIdx.x; t < tEnd; t += blockDim.x) {
     const int k = t / per, r = t - k * per;
     const int y = r >> 1, q = (r & 1) * 4;
     const unsigned long long sl = (unsigned long long)a.slot[k];
@@ -339,7 +344,7 @@ struct wsb_sim {
   unsigned xseq = 0, pending_seq = 0;       // exchanges issued / the one in flight
   unsigned long long spin_ns = kSpinLimitNs;
   int n_sms = 148;
-  int push_blocks = 37;                     // WSB_DBG_PUSH_BLOCKS
+  int push_blocks = 16;                     // CTAs of k_push_ghosts (WSB_DBG_PUSH_BLOCKS): each displaces an advection CTA while it runs — measured 8/16/37/74/148, profiles/r3_multi_gpu.md
   bool dbg_nopush = false;                  // WSB_DBG_NOPUSH: timing experiments only — ghost columns are never refreshed
   cudaEvent_t evEdge = nullptr, evPush = nullptr, evPvbI = nullptr, evPvbE = nullptr, evAdvI = nullptr;
   bool push_pending = false;                // a k_push_ghosts is reading this rank's edge columns

@@ -26,7 +26,7 @@ for line in sass.splitlines():
     if m:
         fn = m.group(1)
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and fn:
         total[fn] += 1
         op = m.group(1).split(".")[0]
