@@ -353,7 +353,7 @@ def run_ours(args):
     sus_sampler = ClockSampler(local_rank)
     _barrier(world)
     sus_sampler.start()
-    batches = _timed_batches(sim, sim.step, K, 3 if args.quick else SUSTAINED_BATCHES, world, device)
+    batches = _timed_batches(sim, sim.step, K, 1 if args.no_prewarm else (3 if args.quick else SUSTAINED_BATCHES), world, device)
     sus_clocks = sus_sampler.result()
     med = float(np.median(batches))
     sustained = {"batches": len(batches), "steps_per_batch": K, "ms_per_step_median": med, "ms_per_step_min": min(batches), "ms_per_step_max": max(batches),
@@ -422,7 +422,7 @@ def run_ours(args):
             ident = {"ok": not bad, "mismatches": bad, "what": f"sha1 of every rank's own columns (base, water, wall, light) after upload + {K} iterations "
                                                                "vs the same run on one GPU (rank 0's device)"}
             del full
-    else:
+    elif not args.no_prewarm:  # (profiler runs skip the long leg)
         e2e_long_s = e2e_run(E2E_LONG_K)
         e2e["k200"] = {"value": W * H * E2E_LONG_K / e2e_long_s, "steps": E2E_LONG_K, "seconds": e2e_long_s,
                        "h2d_bytes_per_step": h2d_total / E2E_LONG_K + 56, "d2h_bytes_per_step": d2h_total / E2E_LONG_K}
@@ -451,8 +451,9 @@ def run_ours(args):
         line["config2_dry_4096x1024"] = dry_sweep_leg(4096, 1024, K, Wm, peak, peak_src, local_rank, prewarm=pre,
                                                       note="working set (4 base planes x 2 copies + wall = 151 MB) is L2-sized (126 MB L2): the HBM roofline fraction is not meaningful here (SURVEY 8d)")
         line["config3_full_8192x2048"] = full_leg(8192, 2048, K, Wm, peak, peak_src, local_rank, prewarm=pre)
-        line["with_particles"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, 1_000_000)
-        line["with_particles_ref_count"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, W * H // 25)
+        line["with_particles"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, 1_000_000, prewarm=pre)
+        if pre:
+            line["with_particles_ref_count"] = particles_leg(W, H, K, Wm, peak, peak_src, local_rank, W * H // 25)
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
     if world > 1:
@@ -491,7 +492,7 @@ def dry_sweep_leg(W, H, K, Wm, peak, peak_src, device_index, prewarm=True, note=
     ms = sim.last_step_ms()
     t, c = sim.kernel_time_ms(S.KERNEL_DRY)
     per = t / max(c, 1)
-    batches = _timed_batches(sim, sim.step_dry, K, SUSTAINED_BATCHES, 1, None)
+    batches = _timed_batches(sim, sim.step_dry, K, SUSTAINED_BATCHES if prewarm else 1, 1, None)
     out = {"value": W * H * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "grid": [W, H],
            "workload": "dry sweep: pressure(prev) + velocity + semi-Lagrangian advection of the base field, one kernel per iteration",
            "roofline": _roofline("k_fused_dry", per, W * H, peak, peak_src, W, H, 1),
@@ -530,7 +531,7 @@ def full_leg(W, H, K, Wm, peak, peak_src, device_index, prewarm=True):
     ms = sim.last_step_ms()
     kt = {n: sim.kernel_time_ms(k) for n, k in (("k_fused_pvb", S.KERNEL_PVB), ("k_fused_adv", S.KERNEL_ADV))}
     dom = max(kt, key=lambda n: kt[n][0])
-    batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES, 1, None)
+    batches = _timed_batches(sim, sim.step, K, SUSTAINED_BATCHES if prewarm else 1, 1, None)
     rl = _roofline(dom, kt[dom][0] / max(kt[dom][1], 1), W * H, peak, peak_src, W, H, 1)
     rl["kernels_ms_per_step"] = {n: t / max(c, 1) for n, (t, c) in kt.items()}
     rl["step_frac_of_104B_roofline"] = (B_ALG_STEP_FULL * W * H / (ms / K * 1e-3) / 1e9) / peak
@@ -542,7 +543,7 @@ def full_leg(W, H, K, Wm, peak, peak_src, device_index, prewarm=True):
     return out
 
 
-def particles_leg(W, H, K, Wm, peak, peak_src, device_index, nd):
+def particles_leg(W, H, K, Wm, peak, peak_src, device_index, nd, prewarm=True):
     """BASELINE config 4: full physics + precipitation particles on one GPU (1 M droplets as named by the config; and the
     W*H/25 droplets the reference itself allocates for this grid, app.js:452,1282)."""
     import wsb200
@@ -557,7 +558,7 @@ def particles_leg(W, H, K, Wm, peak, peak_src, device_index, nd):
     sim.upload(base, water, wall, drops)
     del base, water, wall
     sim.set_profiling(True)
-    sim.step(max(Wm, 30) + PREWARM_ITERS)  # spin-up: the first iterations spawn the bulk of the droplets
+    sim.step(max(Wm, 30) + (PREWARM_ITERS if prewarm else 0))  # spin-up: the first iterations spawn the bulk of the droplets
     sim.sync()
     sampler = ClockSampler(device_index)
     sampler.start()

@@ -24,10 +24,11 @@ def _run(*args, env=None, timeout=600):
     return r.stdout
 
 
-@pytest.mark.parametrize("n,w,h,iters", [(2, 512, 96, 20), (3, 600, 80, 14), (4, 1024, 64, 12), (2, 2304, 160, 9)])
+@pytest.mark.parametrize("n,w,h,iters", [(2, 512, 96, 20), (3, 600, 80, 14), (4, 1024, 64, 12), (2, 2304, 160, 9), (4, 320, 64, 10), (8, 512, 96, 8)])
 def test_strips_in_one_process_bit_identical_to_single_gpu(n, w, h, iters):
     """N sims of one host process linked with plain device pointers: full physics; strip widths that are and are not
-    multiples of the tile width (600 / 3 = 200), strips with and without interior tile columns."""
+    multiples of the tile width (600 / 3 = 200), strips with interior tile columns (two-stream schedule) and strips too
+    narrow to have any (320 / 4 = 80 and 512 / 8 = 64 columns: one launch per kernel, exchange after it)."""
     _run("inproc", n, w, h, iters)
 
 
