@@ -1290,6 +1290,23 @@ int wsb_sync(wsb_sim* s) {
   return strip_checks(s);
 }
 
+int wsb_set_exchange(wsb_sim* s, int32_t transport) {
+  if (!s) return fail("wsb_set_exchange: null sim");
+  if (s->cfg.n_ranks <= 1) return fail("wsb_set_exchange: not a strip of a multi-GPU run");
+  if (use_device(s) || join_exchange(s) || join_push(s)) return 1;
+  CK(cudaStreamSynchronize(s->stream));
+  if (transport == WSB_EXCHANGE_PEER) {
+    if (!s->peerL || !s->peerR) return fail("wsb_set_exchange: the peer transport needs wsb_connect_peers first");
+    s->peer_mode = true;
+  } else if (transport == WSB_EXCHANGE_NCCL) {
+    if (!s->comm) return fail("wsb_set_exchange: the NCCL transport needs a comm_id at wsb_create");
+    s->peer_mode = false;
+  } else {
+    return fail("wsb_set_exchange: unknown transport %d", transport);
+  }
+  return 0;
+}
+
 int wsb_peer_info(wsb_sim* s, uint8_t out[WSB_PEER_INFO_BYTES]) {
   if (!s || !out) return fail("wsb_peer_info: null argument");
   if (s->cfg.n_ranks <= 1 || !s->arena) return fail("wsb_peer_info: not a strip of a multi-GPU run");
@@ -1312,7 +1329,7 @@ int wsb_peer_info(wsb_sim* s, uint8_t out[WSB_PEER_INFO_BYTES]) {
 int wsb_connect_peers(wsb_sim* s, const uint8_t* left, const uint8_t* right) {
   if (!s || !left || !right) return fail("wsb_connect_peers: null argument");
   if (s->cfg.n_ranks <= 1 || !s->arena) return fail("wsb_connect_peers: not a strip of a multi-GPU run");
-  if (s->peer_mode) return fail("wsb_connect_peers: already connected");
+  if (s->peerL || s->peerR) return fail("wsb_connect_peers: already connected");
   if (use_device(s)) return 1;
   PeerInfo L, R;
   memcpy(&L, left, sizeof(L));

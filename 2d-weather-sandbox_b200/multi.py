@@ -39,10 +39,40 @@ def connect_ring(sim, group=None) -> None:
     sim.connect_peers(infos[left], infos[right])
 
 
+def calibrate_exchange(sim, iters: int = 12, group=None) -> dict:
+    """Time `iters` iterations of the LIVE state with each ghost-exchange transport of a strip that has both
+    (transport "auto"), max over ranks, and keep the faster one.  Which one wins depends on the strip width — measured
+    on one NVSwitch box: the peer push at 2 and 8 GPUs, NCCL send/recv at 4 (profiles/r3_multi_gpu.md) — and both
+    give bit-identical fields, so this is a pure scheduling decision.  Advances the simulation by 4 * iters
+    iterations; every rank must call it at the same point.  Returns the timings (ms per iteration)."""
+    import torch
+    import torch.distributed as dist
+
+    if getattr(sim, "transports", None) != ("peer", "nccl"):
+        return {}
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    out = {}
+    for name in ("nccl", "peer"):
+        sim.set_exchange(name)
+        sim.step(iters)  # settle into the transport's steady state
+        sim.sync()
+        dist.barrier(group)
+        sim.step(iters)
+        sim.sync()
+        t = torch.tensor([sim.last_step_ms() / iters], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        out[name] = float(t.item())
+    best = min(out, key=out.get)
+    sim.set_exchange(best)
+    out["chosen"] = best
+    return out
+
+
 def create_distributed(width: int, height: int, *, device: int, gui_controls=None, group=None, transport: str | None = None, **kw):
     """A Simulation for this rank's strip of a width x height grid (torch.distributed must be
     initialised; with world size 1 this is a plain single-GPU simulation).  transport: "peer"
-    (default; WSB_EXCHANGE overrides) or "nccl"."""
+    (default; WSB_EXCHANGE overrides), "nccl", or "auto" = both set up, peer selected until
+    calibrate_exchange(sim) has timed them on the live state."""
     import os
 
     import torch.distributed as dist
@@ -54,23 +84,28 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
     if n == 1:
         return Simulation(width, height, kw.pop("n_droplets", 0), device=device, gui_controls=gui_controls, **kw)
     transport = transport or os.environ.get("WSB_EXCHANGE", "peer")
-    if transport not in ("peer", "nccl"):
+    if transport not in ("peer", "nccl", "auto"):
         raise ValueError(f"unknown ghost-exchange transport {transport!r}")
     kw.pop("n_droplets", None)
     if transport == "nccl":
         cid = broadcast_comm_id(comm_id_create, group)
-        return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+        sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+        sim.transport, sim.transports = "nccl", ("nccl",)
+        return sim
     # peer transport; if any rank cannot map its neighbours (no peer access between the devices, IPC disabled in a
     # container) EVERY rank falls back to the NCCL transport — loudly
+    cid = broadcast_comm_id(comm_id_create, group) if transport == "auto" else None
     sim, err = None, None
     try:
-        sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=None, gui_controls=gui_controls, **kw)
+        sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
         connect_ring(sim, group)
     except Exception as e:  # noqa: BLE001 — collected and agreed on below
         err = repr(e)
     errs = [None] * n
     dist.all_gather_object(errs, err, group=group)
     if all(e is None for e in errs):
+        sim.transport = "peer"
+        sim.transports = ("peer", "nccl") if transport == "auto" else ("peer",)
         return sim
     if sim is not None:
         sim.close()
@@ -81,7 +116,9 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
 
         warnings.warn(f"wsb200: peer-memory ghost exchange unavailable ({[e for e in errs if e][0]}); using ncclSend/ncclRecv")
     cid = broadcast_comm_id(comm_id_create, group)
-    return Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+    sim = Simulation(width, height, 0, device=device, rank=r, n_ranks=n, comm_id=cid, gui_controls=gui_controls, **kw)
+    sim.transport, sim.transports = "nccl", ("nccl",)
+    return sim
 
 
 def gather_strips(local: np.ndarray, width: int, group=None):

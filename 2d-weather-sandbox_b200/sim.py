@@ -68,7 +68,7 @@ def library_path() -> str:
 
 # every symbol include/wsb200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "wsb_comm_id_create", "wsb_peer_info", "wsb_connect_peers", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
+    "wsb_comm_id_create", "wsb_peer_info", "wsb_connect_peers", "wsb_set_exchange", "wsb_create", "wsb_destroy", "wsb_upload", "wsb_upload_local", "wsb_get_layout",
     "wsb_set_profiling", "wsb_kernel_time_ms", "wsb_set_params",
     "wsb_set_profiles", "wsb_set_frame_inputs", "wsb_step", "wsb_sync", "wsb_debug_run_pass",
     "wsb_step_dry", "wsb_read_rect", "wsb_read_points", "wsb_read_droplets", "wsb_get_inactive_droplets",
@@ -94,6 +94,7 @@ def load_library():
     L.wsb_create.argtypes = [ctypes.POINTER(WsbConfig), ctypes.POINTER(vp)]
     L.wsb_peer_info.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8)]
     L.wsb_connect_peers.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+    L.wsb_set_exchange.argtypes = [vp, i32]
     L.wsb_destroy.argtypes = [vp]
     L.wsb_upload.argtypes = [vp, vp, vp, vp, vp]
     L.wsb_upload_local.argtypes = [vp, vp, vp, vp, vp]
@@ -214,6 +215,11 @@ class Simulation:
         if len(left_info) != PEER_INFO_BYTES or len(right_info) != PEER_INFO_BYTES:
             raise WsbError("connect_peers: blobs must come from peer_info()")
         self._check(self.L.wsb_connect_peers(self.h, left_info, right_info))
+
+    def set_exchange(self, transport: str):
+        """Select the ghost-exchange transport ("peer" or "nccl") of a strip that has both."""
+        self._check(self.L.wsb_set_exchange(self.h, {"nccl": 0, "peer": 1}[transport]))
+        self.transport = transport
 
     # -- state ---------------------------------------------------------------------------------
     def upload(self, base, water, wall, drops=None):

@@ -291,7 +291,7 @@ def run_ours(args):
     W, H = args.width, args.height
     K, Wm = args.steps, max(args.warmup, 3)
     peak, peak_src = _peaks()
-    transport = os.environ.get("WSB_EXCHANGE", "peer")
+    transport = os.environ.get("WSB_EXCHANGE", "auto")
 
     g = P.resolve_settings(None)
     g["enablePrecipitation"] = False
@@ -313,6 +313,11 @@ def run_ours(args):
     if not args.no_prewarm:  # a FIXED count: every rank must run the same number of halo exchanges
         sim.step(PREWARM_ITERS)
         sim.sync()
+    calibration = None
+    if world > 1 and transport == "auto":  # both transports are set up: time them on the live state, keep the faster (untimed)
+        calibration = wsb200.multi.calibrate_exchange(sim)
+    if world > 1:
+        transport = getattr(sim, "transport", transport)
     sim.step(Wm)
     sim.sync()
     sampler = ClockSampler(local_rank)  # NVML initialisation takes tens of ms, differently on every rank: BEFORE the barrier —
@@ -438,6 +443,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"full physics {W}x{H} fp32 (pressure+velocity+vorticity+boundary+advection+condensation+lighting), no particles",
                        "grid": [W, H], "partition": partition, "transport": transport if world > 1 else None,
+                       "transport_calibration_ms_per_step": calibration,
                        "schedule": "fused: k_fused_pvb + k_fused_adv per iteration (TMA-staged channel planes)", "prewarm": f"{PREWARM_ITERS} untimed iterations before the W warm-up steps (SM clock ramp-up after host-side state generation)", "l2": "no flush: every plane is >= 256 MiB, far larger than the 126 MB L2",
                        "max_abs_velocity_cells_per_iter": vmax, "state_finite": finite},
             "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline}

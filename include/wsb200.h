@@ -150,6 +150,14 @@ int wsb_comm_id_create(uint8_t out[WSB_COMM_ID_BYTES]);
 int wsb_peer_info(wsb_sim* sim, uint8_t out[WSB_PEER_INFO_BYTES]);
 int wsb_connect_peers(wsb_sim* sim, const uint8_t* left_info, const uint8_t* right_info);
 
+/* A strip created with a comm_id AND linked with wsb_connect_peers has both transports; this selects the one the
+ * following iterations use (every rank must make the same call between the same two iterations; results are
+ * bit-identical either way).  Which one is faster depends on the strip width — measured on one NVSwitch box: peer at
+ * 2 and 8 GPUs, NCCL at 4 (profiles/r3_multi_gpu.md) — so the Python host times both on the live state
+ * (multi.calibrate_exchange).  Synchronises. */
+enum { WSB_EXCHANGE_NCCL = 0, WSB_EXCHANGE_PEER = 1 };
+int wsb_set_exchange(wsb_sim* sim, int32_t transport);
+
 /* app.js:5149-5317 + 4885-5002: allocate state; light, feedback, deposition, lightning, curl and
  * vortForce start zero-filled (texImage2D(..., null)); iterNum = 0, even = true. */
 int wsb_create(const wsb_config* cfg, wsb_sim** out);

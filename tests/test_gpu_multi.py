@@ -31,7 +31,14 @@ def _worker(rank, world, port, W, H, iters, ret, transport):
         g["enablePrecipitation"] = False
         sim = wsb200.multi.create_distributed(W, H, device=rank, gui_controls=g, transport=transport)
         sim.upload(base, water, wall, None)
-        sim.step(iters)
+        if transport == "auto":  # both transports set up; switching between them mid-run must not change a bit
+            sim.step(iters // 2)
+            timings = wsb200.multi.calibrate_exchange(sim, iters=2)
+            assert timings["chosen"] in ("peer", "nccl") and sim.transport == timings["chosen"]
+            sim.set_exchange("nccl" if timings["chosen"] == "peer" else "peer")
+            sim.step(iters - iters // 2 - 8)   # calibrate_exchange advanced 4 * 2 iterations
+        else:
+            sim.step(iters)
         S = wsb200.sim
         x0, lw = sim.strip()
         out = {}
@@ -46,7 +53,7 @@ def _worker(rank, world, port, W, H, iters, ret, transport):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer", "nccl", "auto"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_strips_bit_identical_to_single_gpu(world, transport, tmp_path):
     import torch
