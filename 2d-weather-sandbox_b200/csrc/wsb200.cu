@@ -252,6 +252,17 @@ __global__ void k_wait_ghosts(unsigned* myFlags, unsigned seq, unsigned long lon
   wait_flag(myFlags + kFlagDataR * kFlagStride, seq, myFlags + kFlagErr * kFlagStride, spinNs);
 }
 
+// NaN / Inf scan (debug aid; the reference only has the local NaN-avoidance resets of advectionShader.frag:387-397)
+__global__ void k_count_nonfinite(Planes4 a, Planes4 b, size_t n, unsigned long long* __restrict__ out) {
+  unsigned c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) c += (isfinite(a.c[k][i]) ? 0u : 1u) + (isfinite(b.c[k][i]) ? 0u : 1u);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
 // n scattered texels of one RGBA32F field -> dense float4 array (weather-station style probes);
 // applyPressure: the field is the fused schedule's base_1 with the pressure pass still pending
 __global__ void k_gather_points(GlobalCtx c, Planes4 field, int applyPressure, int n, const int* __restrict__ xy, int lx_off,
@@ -1540,6 +1551,22 @@ int wsb_get_max_velocity(wsb_sim* s, float* out) {
   CK(cudaMemcpyAsync(&u, s->maxv, 4, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   memcpy(out, &u, 4);
+  return 0;
+}
+
+int wsb_count_nonfinite(wsb_sim* s, int64_t* out) {
+  if (!s || !out) return fail("wsb_count_nonfinite: null argument");
+  if (use_device(s)) return 1;
+  if (need_scratch(s, 1)) return 1;
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(s->scratch);
+  CK(cudaMemsetAsync(d, 0, 8, s->stream));
+  const int b = s->schedule == WSB_SCHEDULE_FUSED ? 1 : 0;  // the canonical copy of the schedule (ghost columns included)
+  k_count_nonfinite<<<s->n_sms * 8, 256, 0, s->stream>>>(s->base[b].p, s->water[b].p, cells(s), d);
+  LAUNCHED("k_count_nonfinite");
+  unsigned long long v = 0;
+  CK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  *out = (int64_t)v;
   return 0;
 }
 

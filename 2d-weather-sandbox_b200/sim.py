@@ -73,7 +73,7 @@ EXPORTS = [
     "wsb_set_profiles", "wsb_set_frame_inputs", "wsb_step", "wsb_sync", "wsb_debug_run_pass",
     "wsb_step_dry", "wsb_read_rect", "wsb_read_points", "wsb_read_droplets", "wsb_get_inactive_droplets",
     "wsb_get_lightning", "wsb_get_iter", "wsb_set_iter", "wsb_get_strip", "wsb_get_max_velocity",
-    "wsb_get_launch_count", "wsb_last_step_ms", "wsb_last_error", "wsb_build_info",
+    "wsb_get_launch_count", "wsb_count_nonfinite", "wsb_last_step_ms", "wsb_last_error", "wsb_build_info",
 ]
 
 
@@ -118,6 +118,7 @@ def load_library():
     L.wsb_get_strip.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.wsb_get_max_velocity.argtypes = [vp, f32p]
     L.wsb_get_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+    L.wsb_count_nonfinite.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
     L.wsb_last_step_ms.argtypes = [vp, f32p]
     L.wsb_last_error.restype = ctypes.c_char_p
     L.wsb_build_info.restype = ctypes.c_char_p
@@ -403,6 +404,12 @@ class Simulation:
     def launch_count(self) -> int:
         v = ctypes.c_int64()
         self._check(self.L.wsb_get_launch_count(self.h, ctypes.byref(v)))
+        return v.value
+
+    def count_nonfinite(self) -> int:
+        """NaN / Inf values in the current base and water fields (debug aid)."""
+        v = ctypes.c_int64()
+        self._check(self.L.wsb_count_nonfinite(self.h, ctypes.byref(v)))
         return v.value
 
     def last_step_ms(self) -> float:

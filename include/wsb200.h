@@ -261,6 +261,11 @@ int wsb_get_strip(wsb_sim* sim, int32_t* x_begin, int32_t* local_width);
  * exceeded, instead of returning silently diverged fields. */
 int wsb_get_max_velocity(wsb_sim* sim, float* out);
 
+/* Debug aid: number of NaN / Inf values in the current base and water fields of this rank (the
+ * reference has no failure detection beyond the local NaN-avoidance resets of advectionShader.frag:387-397).
+ * Synchronises. */
+int wsb_count_nonfinite(wsb_sim* sim, int64_t* out);
+
 /* Number of kernels launched by this sim since creation (bench evidence). */
 int wsb_get_launch_count(wsb_sim* sim, int64_t* out);
 

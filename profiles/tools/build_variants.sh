@@ -12,9 +12,7 @@ build() {  # name, flags
   grep -A2 "k_fused_dry" "gpurun_in/libwsb200_$1.so.log" | grep -E "Used|spill" | tr -s ' ' | tr '\n' ' '
   echo
 }
-build pairadv4 "-DWSB_DRY_PAIRADV=1"
-build pairadv3 "-DWSB_DRY_PAIRADV=1 -DWSB_DRY_CTAS=3"
-build pairadv3t32 "-DWSB_DRY_PAIRADV=1 -DWSB_DRY_CTAS=3 -DWSB_DRY_TY=32"
+# (round 2: the two-cells-per-thread advection variants (WSB_DRY_PAIRADV) and the 16-byte sweeps (WSB_SWEEP_QUAD) were timed —
+#  profiles/r3_logs/c1_variants.log: 27-66 % and 2 % slower — and removed from the sources)
 build ty24 "-DWSB_DRY_TY=24"
-build quad "-DWSB_SWEEP_QUAD=1"
 build fma "-DWSB_EXP_FMAMIX"   # timing only: NOT the frozen arithmetic

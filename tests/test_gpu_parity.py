@@ -481,6 +481,22 @@ def test_save_round_trip_through_gpu(save100):
     sim.close()
 
 
+def test_nonfinite_scan(save100):
+    """wsb_count_nonfinite: a clean run holds no NaN / Inf; poisoned texels are counted and, in the air, spread."""
+    sim = wsb200.Simulation.from_save(save100)
+    sim.step(5)
+    assert sim.count_nonfinite() == 0
+    base = save100.base.copy()
+    air = np.argwhere(save100.wall[..., 1] != 0)
+    for (y, x), v in zip(air[[10, 500, 2000]], (np.nan, np.inf, -np.inf)):
+        base[y, x, 3] = v
+    sim.upload(base, save100.water, save100.wall, save100.droplets)
+    assert sim.count_nonfinite() == 3
+    sim.step(3)
+    assert sim.count_nonfinite() > 3
+    sim.close()
+
+
 def test_upload_resets_like_a_page_load(save100):
     sim = wsb200.Simulation.from_save(save100)
     sim.step(25)
