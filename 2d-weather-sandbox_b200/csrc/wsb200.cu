@@ -804,6 +804,7 @@ int make_map(wsb_sim* s, CUtensorMap* m, void* plane, bool isInt, int boxW, int 
   const cuuint64_t strides[1] = {(cuuint64_t)s->pitch * 4};
   const cuuint32_t box[2] = {(cuuint32_t)boxW, (cuuint32_t)boxH};
   const cuuint32_t estr[2] = {1, 1};
+  // (L2 promotion none / 128 B / 256 B: no difference on any kernel, profiles/r3_logs/c28_variants.log)
   CUresult r = g_encode(m, isInt ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

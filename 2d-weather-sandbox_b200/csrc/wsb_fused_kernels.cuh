@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(kNT, 3) k_fused_adv(const __grid_constant__ Gl
     const float fragCoordX = gxf + 0.5f;
     const float texCoordX = fragCoordX * g.texelX;
     const int lxBase = tx + kHX;
-#pragma unroll 1
+#pragma unroll 1  // (two cells in flight per thread, unroll 2: adv +8 % slower at 80 registers, profiles/r3_logs/c28_variants.log)
     for (int ty = ty0; ty < kTY; ty += kRowStep) {
       const int y = Y0 + kH2 + ty;
       if (y >= g.H) break;

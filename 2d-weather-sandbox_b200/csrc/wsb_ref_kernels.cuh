@@ -23,6 +23,7 @@ struct Planes4 {  // one RGBA32F texture as four channel planes
   // cell indices are 32-bit (wsb_create caps the grid at 2^30 cells): an unsigned index lets the
   // compiler address every plane as [uniform 64-bit base + 32-bit register offset]
   __device__ __forceinline__ float4 ld(size_t i) const { return make_float4(c[0][i], c[1][i], c[2][i], c[3][i]); }
+  // (streaming / evict-first stores, __stcs: no difference on any kernel, profiles/r3_logs/c28_variants.log)
   __device__ __forceinline__ void st(size_t i, float4 v) const { c[0][i] = v.x; c[1][i] = v.y; c[2][i] = v.z; c[3][i] = v.w; }
 };
 
