@@ -139,6 +139,41 @@ def _ncu_traffic(kernel: str, W: int, H: int, world: int):
     return None
 
 
+def _p2p_attrs(dev: int, peers):
+    """cudaDeviceGetP2PAttribute of this rank's device towards its ring neighbours: performance rank, access, native
+    atomics (1 over NVLink, 0 over PCIe) — recorded because the peer transport's 32-byte stores crawl over PCIe P2P."""
+    import ctypes
+
+    out = {}
+    try:
+        rt = None
+        for name in ("libcudart.so", "libcudart.so.12", "libcudart.so.13"):
+            try:
+                rt = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if rt is None:
+            import glob
+
+            import torch
+
+            cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+            rt = ctypes.CDLL(cands[0])
+        for p in sorted(set(peers)):
+            if p == dev:
+                continue
+            vals = {}
+            for attr, key in ((1, "performance_rank"), (2, "access"), (3, "native_atomics")):
+                v = ctypes.c_int(-1)
+                rc = rt.cudaDeviceGetP2PAttribute(ctypes.byref(v), attr, dev, p)
+                vals[key] = v.value if rc == 0 else f"error {rc}"
+            out[f"{dev}->{p}"] = vals
+    except Exception as e:  # diagnostics only
+        out["error"] = repr(e)
+    return out
+
+
 def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -350,7 +385,8 @@ def run_ours(args):
         import torch.distributed as dist
 
         per_rank = [None] * world
-        dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": ms_mine / K, "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
+        dist.all_gather_object(per_rank, {"rank": rank, "ms_per_step": ms_mine / K,
+                                          "p2p": _p2p_attrs(local_rank, [(local_rank - 1) % world, (local_rank + 1) % world]), "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"),
                                           **{n: round(t / K, 4) for n, (t, c) in kt.items()}})
         roofline["per_rank"] = per_rank
 
