@@ -5,21 +5,28 @@
 // libwsb200.so; nothing in the product may link, import or call it (only tests/, bench.py's
 // cpu_baseline / --impl reference leg and __graft_entry__.smoke()).
 //
-// PARITY: PINNED TO REFERENCE OUTPUT WHERE THE REFERENCE PRODUCED ANY; the fp32 trajectory itself is UNPINNED.
+// PARITY: PINNED — to the reference's own shader code, executed, and to reference output.
 // The reference ships no tests, golden vectors or expected outputs for this path and its own
-// implementation (GLSL ES 3.00 under a browser) cannot be executed in this environment (no node / browser / GL /
-// SwiftShader), so the oracle is written from the shader sources alone, one function per reference pass, each
-// citing the file:line it follows.  What the reference DID produce are its 14 shipped saves (frameBuff_0 read back
-// from the GPU, app.js:6575-6628).  tests/test_reference_saves.py holds the oracle to them: the integer wall planes
-// TYPE / DISTANCE / VERT_DISTANCE of every save are a fixed point of one more oracle iteration (0 changed bytes; only
-// LAND <-> FIRE flips in burning saves), the vegetation of every land surface cell is unchanged outside a growth tick
-// and the cells that do change are exactly the derived copies an older shader revision left stale, reference-written
-// invariants (wall marker, T == 1000, water-surface clamp, zero wall velocity) survive, and one iteration moves the
-// fp32 fields by the small fractions a running simulation moves (DESIGN.md 6 has the numbers).  NOT pinned: the fp32
-// values after N iterations of the WebGL path — nothing reference-produced exists to compare them with; there every
-// pass is reproduced bit for bit by a second, independent Python restatement of its shader
-// (tests/test_oracle_numpy_*.py, tests/test_oracle_python_*.py), which catches transcription slips and
-// disagreements between two readings of the GLSL, not a shared misreading of what a WebGL implementation does.
+// implementation (GLSL ES 3.00 under a browser) cannot run in this environment as it stands (no node / browser / GL).
+// (1) oracle/_ref: oracle/ref_shim/ translates the reference's GLSL files mechanically (literal suffixes, globals ->
+// struct members, nothing restated) from the checkout where they lie and compiles them for the host against a small
+// GLSL-in-C++ header; the draw loop of app.js:5830-6005 is restated beside them.  tests/test_ref_shaders.py: every
+// pass of this oracle equals the reference's shader of the same name BIT FOR BIT on all 14 shipped saves; whole runs
+// (up to 300 iterations, particles on) on power-of-two crops of shipped saves, every brush / wall tool and the
+// airplane, the particle life cycle, lightning, the slow processes at iteration multiples and the setup generator are
+// bit-identical; BASELINE config 1 (the 100 x 100 save, 1000 iterations) ends with base / water / wall / droplets
+// bit-identical.  The one quantity that is not: SUNLIGHT on grids whose 1 / size is not a power of two, where the
+// hardware LINEAR fetch position is rounded in normalised (shader) vs pixel (frozen) coordinates — an
+// ulp of the row number, below the 8-bit weights of real hardware.  tests/golden/ref_shader_golden.npz carries
+// vectors produced by those shaders to the GPU box (tests/test_ref_shader_golden.py).
+// (2) the 14 shipped saves are the reference's WebGL output (frameBuff_0 read back, app.js:6575-6628);
+// tests/test_reference_saves.py: their integer wall planes TYPE / DISTANCE / VERT_DISTANCE are a fixed point of one
+// more oracle iteration (0 changed bytes; only LAND <-> FIRE flips in burning saves), land-surface vegetation is
+// unchanged outside a growth tick, reference-written invariants survive.
+// (3) every pass is also reproduced bit for bit by a second, independent Python restatement of its shader
+// (tests/test_oracle_numpy_*.py, tests/test_oracle_python_*.py).
+// What remains outside: the behaviour of a particular WebGL implementation where GLSL ES leaves it open (precision of
+// pow / sin, texture filtering weights, point rasterisation) — frozen canonically, see below.
 // Where GLSL/WebGL leaves behaviour implementation-defined the canonical choice is written next to the code (and
 // listed in DESIGN.md "Spec freeze").
 //
