@@ -8,8 +8,10 @@ glsl_shim.h + ref_driver.cpp.  TEST INFRASTRUCTURE.  Outputs only under oracle/_
 Returns 0 and does nothing when the checkout is absent (the GPU box): tests that need the library skip there
 and use the golden vectors generated from it (tests/golden/make_ref_shader_golden.py) instead."""
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "_ref")
@@ -28,9 +30,16 @@ def build(ref_root: str = "/root/reference", force: bool = False) -> str | None:
     srcs += [os.path.join(dp, f) for dp, _, fs in os.walk(shaders) for f in fs]
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in srcs):
         return LIB
-    gen = os.path.join(OUT, "gen")
-    subprocess.check_call([sys.executable, os.path.join(HERE, "translate.py"), shaders, gen], stdout=subprocess.DEVNULL)
-    subprocess.check_call([CXX] + FLAGS + ["-I", HERE, "-I", gen, "-o", LIB, os.path.join(HERE, "ref_driver.cpp")])
+    os.makedirs(OUT, exist_ok=True)
+    gen = tempfile.mkdtemp(prefix="wsb_ref_gen_")  # the translated shader text is an intermediate: only the .so is kept
+    try:
+        subprocess.check_call([sys.executable, os.path.join(HERE, "translate.py"), shaders, gen], stdout=subprocess.DEVNULL)
+        subprocess.check_call([CXX] + FLAGS + ["-I", HERE, "-I", gen, "-o", LIB, os.path.join(HERE, "ref_driver.cpp")])
+    finally:
+        if os.environ.get("WSB_KEEP_REF_GEN"):
+            print("generated headers kept in", gen)
+        else:
+            shutil.rmtree(gen, ignore_errors=True)
     return LIB
 
 

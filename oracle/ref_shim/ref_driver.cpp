@@ -3,7 +3,7 @@
 // The twelve gen_*.h headers included below are produced at build time by translate.py from the GLSL files
 // where they lie in the reference checkout (shaders/common.glsl, vertex/simShader.vert, fragment/{velocity,
 // curl,vorticity,boundary,advection,pressure,lighting,lightningLocation,precipitation,setup}Shader.frag,
-// vertex/precipitationShader.vert) and compiled against glsl_shim.h; they are build artefacts under oracle/_ref/
+// vertex/precipitationShader.vert) and compiled against glsl_shim.h; they are intermediates of the build (a temporary directory; only the .so is kept, under oracle/_ref/)
 // and never enter the repository.  This file is the part of the reference that is JavaScript and therefore has
 // to be restated: the GL objects of app.js:5118-5317 (textures and their sampling state), the sampler -> texture
 // unit assignments of app.js:5486-5640, the draw loop of app.js:5830-6005 (which texture is bound to which unit
