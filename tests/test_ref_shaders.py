@@ -100,7 +100,8 @@ def crop_pow2(sf, x0, w, h):
 @pytest.mark.parametrize("path", SAVES, ids=[os.path.basename(p)[:-len(".weathersandbox")] for p in SAVES])
 def test_every_pass_on_every_shipped_save(path):
     """Each pass of two iterations, with the reference shaders started from the oracle's complete state before
-    every pass: identical inputs, outputs compared bit for bit (SUNLIGHT: module docstring)."""
+    every pass (second iteration: before its first pass): identical inputs, outputs compared bit for bit (SUNLIGHT:
+    module docstring)."""
     sf = wsb200.savefile.load(path)
     g = P.resolve_settings(sf.settings_json)
     ora = make_oracle(g, sf.base, sf.water, sf.wall, sf.droplets)
@@ -108,7 +109,10 @@ def test_every_pass_on_every_shipped_save(path):
     pow2 = (sf.width & (sf.width - 1)) == 0 and (sf.height & (sf.height - 1)) == 0
     for it in range(2):
         for p, name in enumerate(PASS_NAMES):
-            ref.copy_state_from(ora)
+            # iteration 0: identical inputs before EVERY pass; iteration 1: before the first only (the one tolerated
+            # difference, SUNLIGHT, appears in the lighting pass and nothing after it in the iteration reads the light)
+            if it == 0 or p == 0:
+                ref.copy_state_from(ora)
             ora.run_pass(p)
             ref.run_pass(p)
             bad = differences(ora, ref, sun_tolerance=not pow2)
