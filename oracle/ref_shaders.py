@@ -1,9 +1,11 @@
 """ctypes wrapper of oracle/_ref/libref_shaders.so — the reference's OWN GLSL simulation shaders, translated
 mechanically from the reference checkout and compiled for the host (oracle/ref_shim/).  TEST INFRASTRUCTURE ONLY:
-imported by tests/ and tests/golden/make_ref_shader_golden.py, never by the product, bench.py or smoke().
+imported by tests/, tests/golden/make_ref_shader_golden.py and bench.py's CPU legs (cpu_baseline / --impl reference,
+where it is the thing timed as "the reference on the host cores"), never by the product or smoke().
 
-The library exists only where the reference checkout does (this container); `available()` is False on the GPU
-box, where the committed golden vectors generated from it stand in (tests/golden/ref_shader_*.npz).
+The library is BUILT only where the reference checkout is (this container); like the other built .so files it is
+git-ignored but travels to the GPU box with the snapshot, where `available()` then finds the prebuilt file.  Without it
+the committed golden vectors generated from it stand in (tests/golden/ref_shader_golden.npz) and bench.py times the port.
 
 RefShaderSim has the interface of oracle.OracleSim (same field / pass ids), so a test can drive both side by side."""
 from __future__ import annotations
@@ -91,7 +93,7 @@ class RefShaderSim:
         self.W, self.H, self.ND = width, height, n_droplets
         h = self.L.refsim_create(width, height, n_droplets)
         if not h:
-            raise ValueError("the reference's uniform arrays hold 504 rows: height must be <= 503")
+            raise ValueError("height beyond the per-row uniform tables of the build (WSB_REF_MAX_ROWS, glsl_shim.h)")
         self.h = ctypes.c_void_p(h)
 
     def close(self):
@@ -195,7 +197,7 @@ class RefShaderSim:
 def setup_state(width: int, height: int, seed: float, height_mult: float, sim_height: float, dry_lapse: float, initial_T):
     """setupShader.frag drawn once into frameBuff_0 (app.js:5729-5742): (base, water, wall)."""
     initial_T = np.ascontiguousarray(initial_T, np.float32)
-    assert initial_T.shape == (height + 1,) and height <= 503
+    assert initial_T.shape == (height + 1,)
     base = np.zeros((height, width, 4), np.float32)
     water = np.zeros((height, width, 4), np.float32)
     wall = np.zeros((height, width, 4), np.int8)

@@ -19,7 +19,7 @@ LIB = os.path.join(OUT, "libref_shaders.so")
 CXX = "/usr/bin/g++"  # the image's $CXX wrapper has no libgomp.spec (see oracle/Makefile)
 # -ffp-contract=off: one fp32 rounding per written operation.  -fpermissive: GLSL lets a `case` label jump over a
 # declaration with an initialiser (boundaryShader.frag:437, lightingShader.frag:103), C++ calls that ill-formed.
-FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fpermissive", "-w"]
+FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fpermissive", "-w"]
 
 
 def build(ref_root: str = "/root/reference", force: bool = False) -> str | None:

@@ -16,6 +16,10 @@
 #include <cstring>
 #include <type_traits>
 
+// bound of the per-row uniform tables (reference: 126 vec4 = 504 rows, which caps its grids at 503 rows)
+#define WSB_REF_PROFILE_VEC4S 1026
+#define WSB_REF_MAX_ROWS (4 * WSB_REF_PROFILE_VEC4S - 1)
+
 namespace glsl {
 
 typedef unsigned int uint;
@@ -223,7 +227,11 @@ inline int operator%(int a, NzInt b) { return b.v == 0 ? 1 : a % b.v; }
 
 // ---- textures ------------------------------------------------------------------------------------------
 enum { GL_NEAREST = 0, GL_LINEAR = 1, GL_REPEAT = 0, GL_CLAMP_TO_EDGE = 1 };
-inline int wrapi(int i, int n) { i %= n; return i < 0 ? i + n : i; }
+inline int wrapi(int i, int n) {
+  if (i >= 0 && i < n) return i;  // the common case: no integer division
+  i %= n;
+  return i < 0 ? i + n : i;
+}
 inline int wrap_mode(int i, int n, int mode) { return mode == GL_REPEAT ? wrapi(i, n) : (i < 0 ? 0 : (i >= n ? n - 1 : i)); }
 
 struct Texture {  // what a texture object holds: storage, size, channels, sampling state (app.js:5189-5317)

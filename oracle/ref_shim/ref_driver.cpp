@@ -72,7 +72,8 @@ struct UniformBag {
   vec2 userInputMove;
   int userInputType;
   bool wrapHorizontally;
-  vec4 initial_Tv[126], realWorldSounding_Tv[126], realWorldSounding_Wv[126], realWorldSounding_Velv[126];
+  vec4 initial_Tv[WSB_REF_PROFILE_VEC4S], realWorldSounding_Tv[WSB_REF_PROFILE_VEC4S], realWorldSounding_Wv[WSB_REF_PROFILE_VEC4S],
+      realWorldSounding_Velv[WSB_REF_PROFILE_VEC4S];
   float simHeight, seed, heightMult;  // setupShader only
 };
 
@@ -83,7 +84,7 @@ struct Sim {
   // texture objects (app.js:5189-5317): storage + sampling state
   Texture tBase[2], tWater[2], tWall[2], tLight[2], tFb, tDep, tCurl, tVort, tLightning;
   const Texture* unit[16];  // gl.activeTexture / gl.bindTexture
-  float initial_T[504], snd_T[504], snd_W[504], snd_Vel[504];
+  float initial_T[4 * WSB_REF_PROFILE_VEC4S], snd_T[4 * WSB_REF_PROFILE_VEC4S], snd_W[4 * WSB_REF_PROFILE_VEC4S], snd_Vel[4 * WSB_REF_PROFILE_VEC4S];
   float inactiveDroplets;  // the uniform, re-sent every 600 iterations (app.js:5957-5967)
   long iter;
   bool even;
@@ -129,7 +130,7 @@ UniformBag make_bag(const Sim& s) {
   u.userInputMove = vec2(s.in.userInputMove[0], s.in.userInputMove[1]);
   u.userInputType = s.in.userInputType;
   u.wrapHorizontally = s.in.wrapHorizontally != 0;
-  for (int i = 0; i < 126; i++) {  // gl.uniform4fv(..., Float32Array(504)) app.js:5476, 5492-5494
+  for (int i = 0; i < WSB_REF_PROFILE_VEC4S; i++) {  // gl.uniform4fv(..., Float32Array(504)) app.js:5476, 5492-5494
     u.initial_Tv[i] = vec4(s.initial_T[4 * i], s.initial_T[4 * i + 1], s.initial_T[4 * i + 2], s.initial_T[4 * i + 3]);
     u.realWorldSounding_Tv[i] = vec4(s.snd_T[4 * i], s.snd_T[4 * i + 1], s.snd_T[4 * i + 2], s.snd_T[4 * i + 3]);
     u.realWorldSounding_Wv[i] = vec4(s.snd_W[4 * i], s.snd_W[4 * i + 1], s.snd_W[4 * i + 2], s.snd_W[4 * i + 3]);
@@ -291,7 +292,7 @@ void iteration(Sim& s) {  // app.js:5830-6005
 extern "C" {
 
 void* refsim_create(int w, int h, int n_droplets) {
-  if (w < 1 || h < 1 || h > 503) return nullptr;  // uniform vec4 initial_Tv[126]: 504 rows at most
+  if (w < 1 || h < 1 || h > WSB_REF_MAX_ROWS) return nullptr;  // uniform vec4 initial_Tv[]: one entry per row + 1
   Sim* s = new Sim();
   s->w = w; s->h = h; s->nd = n_droplets;
   const size_t n = (size_t)w * h;
@@ -330,7 +331,7 @@ void refsim_set_frame_inputs(void* h, const void* in) { memcpy(&((Sim*)h)->in, i
 void refsim_set_profiles(void* h, const float* T0, const float* sT, const float* sW, const float* sV) {
   Sim& s = *(Sim*)h;
   const size_t n = (size_t)s.h + 1;
-  auto put = [&](float* dst, const float* src) { memset(dst, 0, 504 * 4); if (src) memcpy(dst, src, n * 4); };
+  auto put = [&](float* dst, const float* src) { memset(dst, 0, sizeof(s.initial_T)); if (src) memcpy(dst, src, n * 4); };
   if (T0) put(s.initial_T, T0);
   put(s.snd_T, sT); put(s.snd_W, sW); put(s.snd_Vel, sV);
 }
@@ -386,7 +387,7 @@ void refsim_setup(int w, int h, float seed, float heightMult, float simHeight, f
   u.texelSize = vec2((float)(1.0 / (double)w), (float)(1.0 / (double)h));
   u.resolution = vec2((float)w, (float)h);
   u.dryLapse = dryLapse; u.simHeight = simHeight; u.seed = seed; u.heightMult = heightMult;
-  for (int i = 0; i < 126; i++) {
+  for (int i = 0; i < WSB_REF_PROFILE_VEC4S; i++) {
     float t[4];
     for (int k = 0; k < 4; k++) t[k] = (4 * i + k <= h) ? initial_T[4 * i + k] : 0.0f;
     u.initial_Tv[i] = vec4(t[0], t[1], t[2], t[3]);

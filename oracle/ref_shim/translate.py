@@ -12,6 +12,8 @@ mechanically — no shader logic is restated here:
     invocation — zero unless the shader gives an initialiser ("out varyings start at zero", DESIGN.md 2);
   * scalar locals declared without an initialiser start at zero (lightingShader.frag:90 IR_up: undefined in
     GLSL where no case assigns it; canonical 0);
+  * the bound of the per-row uniform tables (`vec4 ...[126]`, 504 rows) is raised to WSB_REF_PROFILE_VEC4S (grids taller
+    than the reference's own 503-row cap: every BASELINE grid); indexing is untouched;
   * every `case` of a `switch` gets its own block (C++ forbids jumping over initialised declarations);
   * the right operand of integer `%` is wrapped in glsl_nz() (`% 0` is undefined in GLSL; canonical "non-zero");
   * the whole shader becomes `struct Shader` in namespace glsl::ref_<name>, with `main()` as a member, plus
@@ -133,6 +135,10 @@ def translate(shader_dir: str, rel: str, ns: str) -> str:
             if m:
                 q, ty, name, arr = m.group(1), m.group(2), m.group(3), m.group(4) or ""
                 if q == "uniform":
+                    if ty == "vec4" and arr.replace(" ", "") == "[126]":
+                        # the per-row profile tables (initial_Tv, realWorldSounding_*v): 504 rows in the reference, which
+                        # caps its grids at 503 rows; the BASELINE grids are taller, so ONLY the array bound is raised
+                        arr = "[WSB_REF_PROFILE_VEC4S]"
                     uniforms.append((ty, name, arr))
                     body.append("  static inline %s %s%s;" % (ty, name, arr))
                 else:
@@ -159,8 +165,8 @@ def translate(shader_dir: str, rel: str, ns: str) -> str:
         if ty in SAMPLERS:
             continue
         if arr:
-            cnt = int(re.sub(r"\D", "", arr))
-            binds.append("for (int i = 0; i < %d; i++) %s[i] = u.%s[i];" % (cnt, name, name))
+            cnt = arr.strip("[] ")
+            binds.append("for (int i = 0; i < %s; i++) %s[i] = u.%s[i];" % (cnt, name, name))
         else:
             binds.append("%s = u.%s;" % (name, name))
     glue.append("  template <class Bag> static void bind_uniforms(const Bag& u) { " + " ".join(binds) + " (void)u; }")

@@ -329,6 +329,25 @@ def test_growth_rates_beyond_100_take_the_canonical_modulo():
         assert not bad, f"from iteration {start}: {bad}"
 
 
+def test_grid_taller_than_the_reference_cap_bit_identical():
+    """512 rows: beyond the 503 the reference's own 126-vec4 profile tables allow.  The translator raises
+    ONLY that array bound (translate.py); the shaders index it as they always did.  A power-of-two stress state, 40
+    iterations with particles: every buffer bit-identical to the oracle, whose tables are sized by the grid."""
+    w, h = 128, 512
+    g, base, water, wall, drops = stress_state(w, h, seed=5)
+    g["enablePrecipitation"] = True
+    ora = make_oracle(g, base, water, wall, drops)
+    ref = make_ref(g, base, water, wall, drops)
+    for n in (1, 9, 30):
+        ora.step(n)
+        ref.step(n)
+        bad = differences(ora, ref)
+        assert not bad, f"iteration {ora.iter}: {bad}"
+    assert np.isfinite(ora.field(O.FIELD_BASE, 0)).all()
+    with pytest.raises(ValueError):
+        R.RefShaderSim(16, 5000)
+
+
 @pytest.mark.parametrize("w,h,seed,mult", [(256, 128, 0.37, 0.5), (300, 100, 0.81, 0.9), (128, 64, 0.5, 0.07), (64, 64, 0.1, 0.01), (1000, 250, 0.2566, 0.33), (2000, 300, 0.37, 1.0)])
 def test_setup_shader_matches_synth_setup_state(w, h, seed, mult):
     """setupShader.frag (the reference's own, compiled) drawn once == synth.setup_state, bit for bit."""
