@@ -22,7 +22,15 @@ CXX = "/usr/bin/g++"  # the image's $CXX wrapper has no libgomp.spec (see oracle
 FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-fpermissive", "-w"]
 
 
-def build(ref_root: str = "/root/reference", force: bool = False) -> str | None:
+def build(ref_root: str = "/root/reference", force: bool = False, extra_flags=(), out: str | None = None) -> str | None:
+    """extra_flags / out: experiment builds (e.g. -DWSB_REF_LIBM, -ffp-contract=fast) beside the canonical library."""
+    global LIB
+    if out is not None:
+        saved, LIB = LIB, out
+        try:
+            return build(ref_root, True, extra_flags)
+        finally:
+            LIB = saved
     shaders = os.path.join(ref_root, "shaders")
     if not os.path.isdir(shaders):
         return LIB if os.path.exists(LIB) else None
@@ -34,7 +42,7 @@ def build(ref_root: str = "/root/reference", force: bool = False) -> str | None:
     gen = tempfile.mkdtemp(prefix="wsb_ref_gen_")  # the translated shader text is an intermediate: only the .so is kept
     try:
         subprocess.check_call([sys.executable, os.path.join(HERE, "translate.py"), shaders, gen], stdout=subprocess.DEVNULL)
-        subprocess.check_call([CXX] + FLAGS + ["-I", HERE, "-I", gen, "-o", LIB, os.path.join(HERE, "ref_driver.cpp")])
+        subprocess.check_call([CXX] + FLAGS + list(extra_flags) + ["-I", HERE, "-I", gen, "-o", LIB, os.path.join(HERE, "ref_driver.cpp")])
     finally:
         if os.environ.get("WSB_KEEP_REF_GEN"):
             print("generated headers kept in", gen)

@@ -169,8 +169,13 @@ inline float floor(float x) { return floorf(x); }
 inline float fract(float x) { return x - floorf(x); }
 inline float mod(float x, float y) { return x - y * floorf(x / y); }
 inline float sqrt(float x) { return sqrtf(x); }
+#ifdef WSB_REF_LIBM
+inline float sin(float x) { return sinf(x); }
+inline float cos(float x) { return cosf(x); }
+#else
 inline float sin(float x) { return (float)::sin((double)x); }  // evaluated in double, rounded once
 inline float cos(float x) { return (float)::cos((double)x); }
+#endif
 inline float step(float e, float x) { return x < e ? 0.0f : 1.0f; }
 inline float smoothstep(float e0, float e1, float x) {
   float t = clamp((x - e0) / (e1 - e0), 0.0f, 1.0f);
@@ -189,6 +194,9 @@ inline float cbrt_canon(float m) {
 }
 // pow with the constant exponents of the simulation shaders as closed forms; anything else: libm
 inline float pow(float x, float y) {
+#ifdef WSB_REF_LIBM  // sensitivity experiment only (profiles/tools/freeze_sensitivity.py): what another implementation's pow would give
+  return powf(x, y);
+#endif
   if (y == 17.0f) { float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8; return x16 * x; }
   if (y == 4.0f) { float x2 = x * x; return x2 * x2; }
   if (y == 2.0f) return x * x;
