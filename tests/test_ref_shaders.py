@@ -20,6 +20,10 @@ of the row / column number, ~3e-5 of a texel) unless the texel size is exact.  R
 to 8 bits (4e-3 of a texel), so neither form is "the" WebGL result; on power-of-two grids they are identical and the
 runs below are bit-exact in every field including the light.
 
+Mutation-checked: six seeded one-token changes of the oracle — a coefficient in the boundary, advection and lighting
+passes and in the precipitation feedback, the wrong neighbour in the pressure pass, an off-by-one in the wall-distance
+propagation — each fail the first save they touch.
+
 Needs the reference checkout (this container); skipped on the GPU box, where tests/golden/ref_shader_*.npz —
 generated from this library by tests/golden/make_ref_shader_golden.py — stand in (tests/test_ref_shader_golden.py)."""
 import glob
@@ -346,6 +350,48 @@ def test_grid_taller_than_the_reference_cap_bit_identical():
     assert np.isfinite(ora.field(O.FIELD_BASE, 0)).all()
     with pytest.raises(ValueError):
         R.RefShaderSim(16, 5000)
+
+
+def test_full_width_grid_coordinate_quantisation_bit_identical():
+    """16384 columns (the BASELINE width) x 64 rows: beyond x = 8192 the fp32 spacing of `fragCoord - v` is 2^-10 of a
+    cell and the back-trace of advectionShader.frag:93-103 / common.glsl:194-254 quantises accordingly (hard
+    part 2) — the oracle, whose large-grid strips are the GPU tests' bar at 16384 x 4096, against the shader code itself."""
+    w, h = 16384, 64
+    g = P.resolve_settings(None)
+    g["dayNightCycle"] = False
+    g["sunAngle"] = 60.0
+    g["enablePrecipitation"] = False
+    base, water, wall, _ = wsb200.synth.full_state(w, h, seed=7, g=g, with_droplets=False, vel_amplitude=0.3)
+    ora = make_oracle(g, base, water, wall, None)
+    ref = make_ref(g, base, water, wall, None)
+    for n in (1, 5):
+        ora.step(n)
+        ref.step(n)
+        bad = differences(ora, ref)
+        assert not bad, f"iteration {ora.iter}: {bad}"
+    moved = ora.field(O.FIELD_BASE, 0)[:, 8192:, :2]
+    assert np.abs(moved).max() > 0.05  # there is flow to trace back in the quantised half
+
+
+@pytest.mark.parametrize("scale", [8.0, 40.0])
+def test_fast_flow_back_trace_bit_identical(scale):
+    """Velocities of 0.45 and 2.3 cells per iteration (the shipped saves peak at 0.36): the back-trace leaves the
+    neighbouring cell, bilerp / bilerpWall fetch texels several cells away and across the periodic seam."""
+    w, h = 256, 64
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=1234)
+    base[..., :2] *= f32(scale)
+    wall[20:30, 60:70, 1] = 0  # a block of wall in the flow: the wall-aware weights of bilerpWall
+    wall[20:30, 60:70, 0] = 1
+    g = P.resolve_settings(None)
+    g["enablePrecipitation"] = False
+    ora = make_oracle(g, base, water, wall, None)
+    ref = make_ref(g, base, water, wall, None)
+    assert np.abs(base[..., :2]).max() > 0.05 * scale
+    for n in (1, 3):
+        ora.step(n)
+        ref.step(n)
+        bad = differences(ora, ref)
+        assert not bad, f"scale {scale}, iteration {ora.iter}: {bad}"
 
 
 @pytest.mark.parametrize("w,h,seed,mult", [(256, 128, 0.37, 0.5), (300, 100, 0.81, 0.9), (128, 64, 0.5, 0.07), (64, 64, 0.1, 0.01), (1000, 250, 0.2566, 0.33), (2000, 300, 0.37, 1.0)])
