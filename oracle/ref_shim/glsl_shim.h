@@ -255,18 +255,24 @@ inline vec4 fetch_f(const Texture& t, int ix, int iy) {  // missing channels rea
   const float* p = t.f + ((size_t)iy * t.W + ix) * t.C;
   return vec4(p[0], t.C > 1 ? p[1] : 0.0f, t.C > 2 ? p[2] : 0.0f, t.C > 3 ? p[3] : 1.0f);
 }
-// NEAREST: texel floor(u * size), fp32.  LINEAR: full-fp32 bilinear about (u * size - 0.5).  A coordinate that
-// is a texel centre up to the rounding of u * size (4 ulp) returns that texel: the IR fetches of
-// lightingShader.frag:88,119 aim at centres, and on grids whose 1 / size is not exact in fp32 the product
-// (x + 0.5) / size * size misses x + 0.5 by an ulp (hardware, with 8-bit weights, cannot see that either).
+// NEAREST: texel floor(u * size), fp32.  LINEAR: full-fp32 bilinear about (u * size - 0.5) — except that a coordinate
+// which IS a texel-centre coordinate, bit for bit as simShader.vert forms them ((i + 0.5) * texelSize, or a
+// neighbour's +- texelSize), fetches that texel: lightingShader.frag:88,119 read IR_DOWN / IR_UP of the cells above
+// and below through the LINEAR light sampler, and on grids whose 1 / size is not exact in fp32 the round trip
+// (i + 0.5) * (1 / size) * size misses i + 0.5 by an ulp, which no hardware (8-bit weights) can see.
+inline bool is_centre_coord(float u, int i, int size) {
+  const float t = (float)(1.0 / (double)size);  // the uniform texelSize (app.js:5436-5437: JS double -> uniform2f)
+  const float c0 = ((float)i + 0.5f) * t, cm = ((float)(i - 1) + 0.5f) * t, cp = ((float)(i + 1) + 0.5f) * t;
+  return u == c0 || u == cm + t || u == cp + (-t);
+}
 inline vec4 texture(sampler2D s, const vec2& uv) {
   const Texture& t = *s.t;
   const float px = uv.x * (float)t.W, py = uv.y * (float)t.H;
   if (t.filter == GL_NEAREST)
     return fetch_f(t, wrap_mode((int)floorf(px), t.W, t.wrapS), wrap_mode((int)floorf(py), t.H, t.wrapT));
   float stx = px - 0.5f, sty = py - 0.5f;
-  if (fabsf(stx - rintf(stx)) <= 4.8e-7f * fabsf(px)) stx = rintf(stx);
-  if (fabsf(sty - rintf(sty)) <= 4.8e-7f * fabsf(py)) sty = rintf(sty);
+  if (is_centre_coord(uv.x, (int)rintf(stx), t.W)) stx = rintf(stx);
+  if (is_centre_coord(uv.y, (int)rintf(sty), t.H)) sty = rintf(sty);
   const float flx = floorf(stx), fly = floorf(sty);
   const float fx = stx - flx, fy = sty - fly;
   const int x0 = wrap_mode((int)flx, t.W, t.wrapS), x1 = wrap_mode((int)flx + 1, t.W, t.wrapS);

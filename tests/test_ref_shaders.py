@@ -17,8 +17,8 @@ One quantity is compared with a tolerance on grids whose 1 / size is not a power
 through the hardware LINEAR fetch of lightingShader.frag:48-49.  The shader forms `texCoord + sunRay` in normalised
 coordinates, the oracle works in pixel space; the two round the sample position differently (by an ulp
 of the row / column number, ~3e-5 of a texel) unless the texel size is exact.  Real hardware quantises that weight
-to 8 bits (4e-3 of a texel), so neither form is "the" WebGL result; on power-of-two grids they are identical and the
-runs below are bit-exact in every field including the light.
+to 8 bits (4e-3 of a texel), so neither form is "the" WebGL result; on power-of-two grids they are identical — at
+every sun angle, tested — and the runs below are bit-exact in every field including the light.
 
 Mutation-checked: six seeded one-token changes of the oracle — a coefficient in the boundary, advection and lighting
 passes and in the precipitation feedback, the wrong neighbour in the pressure pass, an off-by-one in the wall-distance
@@ -392,6 +392,23 @@ def test_fast_flow_back_trace_bit_identical(scale):
         ref.step(n)
         bad = differences(ora, ref)
         assert not bad, f"scale {scale}, iteration {ora.iter}: {bad}"
+
+
+@pytest.mark.parametrize("w,h", [(128, 64), (2048, 32), (64, 1024)])
+def test_sun_fetch_bit_identical_at_every_sun_angle_on_power_of_two_grids(w, h):
+    """The LINEAR fetch `texture(lightTex, texCoord + sunRay)` with the sun at the zenith (ray offset exactly one row),
+    2 degrees off it (an offset a few ulp short of a texel centre at large y), near and below the horizon, from either
+    side: normalised (shader) and pixel-space (frozen) arithmetic give the same bits when 1 / size is a power of two."""
+    for gui_angle in (90.0, 88.0, 60.0, 1.0, -3.0, 172.0):
+        g, base, water, wall, _ = stress_state(w, h, seed=3)
+        g["sunAngle"] = gui_angle
+        g["enablePrecipitation"] = False
+        ora = make_oracle(g, base, water, wall, None)
+        ref = make_ref(g, base, water, wall, None)
+        ora.step(24)
+        ref.step(24)
+        bad = differences(ora, ref)
+        assert not bad, f"{w}x{h}, sun at {gui_angle} degrees: {bad}"
 
 
 @pytest.mark.parametrize("w,h,seed,mult", [(256, 128, 0.37, 0.5), (300, 100, 0.81, 0.9), (128, 64, 0.5, 0.07), (64, 64, 0.1, 0.01), (1000, 250, 0.2566, 0.33), (2000, 300, 0.37, 1.0)])
