@@ -177,7 +177,18 @@ __device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned seq, un
   }
 }
 
+// Landing zones (transport "peerc"): behind the flags every arena holds two COMPACT copies of a ghost zone —
+// [side: 0 = left ghost, 1 = right ghost][plane k of the exchange][row][8 columns] — 32 bytes per (plane, row), 1.7 MB
+// per side at H = 4096 instead of 13 x H rows scattered over every 2-MB page of the planes.  The neighbours store
+// there and the owner copies the zone into its ghost columns locally (k_unpack_zone) once the data flags are up.
+constexpr size_t kZoneOffset = (size_t)kNumFlags * kFlagStride * 4;  // behind the flag lines
+__host__ __device__ __forceinline__ size_t zone_bytes(int H) { return (size_t)2 * kMaxHaloPlanes * H * kGhost * 4; }
+__device__ __forceinline__ int* zone_row(unsigned char* arena, unsigned long long pb, int H, int side, int k, int y) {
+  return reinterpret_cast<int*>(arena + pb * kArenaSlots + kZoneOffset) + (((size_t)side * kMaxHaloPlanes + k) * H + y) * kGhost;
+}
+
 struct PushArgs {
+  int compact;                          // 1: store into the neighbours' landing zones instead of their ghost columns
   unsigned char *mine, *left, *right;   // arenas: this rank's, the neighbours' (peer-mapped)
   unsigned long long pbMine, pbLeft, pbRight;  // bytes per plane slot
   int pitchMine, pitchLeft, pitchRight;
@@ -223,7 +234,20 @@ __global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ Pus
     int* dr = reinterpret_cast<int*>(a.right + sl * a.pbRight) + (size_t)y * a.pitchRight + q;                   // its left ghost zone
     const int* sL = src + kGhost + q;   // my leftmost owned columns
     const int* sR = src + a.lw + q;     // my rightmost owned columns
-    if (a.vec) {
+    if (a.compact) {  // the neighbours' landing zones: always 16-byte aligned
+      dl = zone_row(a.left, a.pbLeft, a.H, 1, k, y) + q;
+      dr = zone_row(a.right, a.pbRight, a.H, 0, k, y) + q;
+      int4 vl, vr;
+      if (a.vec) {
+        vl = *reinterpret_cast<const int4*>(sL);
+        vr = *reinterpret_cast<const int4*>(sR);
+      } else {
+        vl = make_int4(sL[0], sL[1], sL[2], sL[3]);
+        vr = make_int4(sR[0], sR[1], sR[2], sR[3]);
+      }
+      *reinterpret_cast<int4*>(dl) = vl;
+      *reinterpret_cast<int4*>(dr) = vr;
+    } else if (a.vec) {
       *reinterpret_cast<int4*>(dl) = *reinterpret_cast<const int4*>(sL);
       *reinterpret_cast<int4*>(dr) = *reinterpret_cast<const int4*>(sR);
     } else {
@@ -250,6 +274,33 @@ __global__ void __launch_bounds__(256) k_push_ghosts(const __grid_constant__ Pus
 __global__ void k_wait_ghosts(unsigned* myFlags, unsigned seq, unsigned long long spinNs) {
   wait_flag(myFlags + kFlagDataL * kFlagStride, seq, myFlags + kFlagErr * kFlagStride, spinNs);
   wait_flag(myFlags + kFlagDataR * kFlagStride, seq, myFlags + kFlagErr * kFlagStride, spinNs);
+}
+
+// transport "peerc": this rank's landing zones -> its ghost columns (local copy, after k_wait_ghosts in stream order)
+struct UnpackArgs {
+  unsigned char* mine;
+  unsigned long long pb;
+  int pitch, lw, H, vec, n;
+  int slot[13];
+};
+__global__ void __launch_bounds__(256) k_unpack_zone(const __grid_constant__ UnpackArgs a) {
+  const int per = a.H * 2, total = per * a.n;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int k = t / per, r = t - k * per;
+    const int y = r >> 1, q = (r & 1) * 4;
+    int* row = reinterpret_cast<int*>(a.mine + (unsigned long long)a.slot[k] * a.pb) + (size_t)y * a.pitch;
+    const int4 vl = *reinterpret_cast<const int4*>(zone_row(a.mine, a.pb, a.H, 0, k, y) + q);
+    const int4 vr = *reinterpret_cast<const int4*>(zone_row(a.mine, a.pb, a.H, 1, k, y) + q);
+    int* dl = row + q;                   // left ghost zone
+    int* dr = row + kGhost + a.lw + q;   // right ghost zone
+    if (a.vec) {
+      *reinterpret_cast<int4*>(dl) = vl;
+      *reinterpret_cast<int4*>(dr) = vr;
+    } else {
+      dl[0] = vl.x; dl[1] = vl.y; dl[2] = vl.z; dl[3] = vl.w;
+      dr[0] = vr.x; dr[1] = vr.y; dr[2] = vr.z; dr[3] = vr.w;
+    }
+  }
 }
 
 // NaN / Inf scan (debug aid; the reference only has the local NaN-avoidance resets of advectionShader.frag:387-397)
@@ -348,6 +399,8 @@ struct wsb_sim {
   size_t plane_bytes = 0, arena_bytes = 0;
   int wall_slot[2] = {-1, -1};
   bool peer_mode = false;                   // wsb_connect_peers succeeded: k_push_ghosts / k_wait_ghosts instead of NCCL
+  bool peer_compact = false;                // transport "peerc": the push goes through the landing zones (k_unpack_zone after the wait)
+  bool pend_compact = false; int pend_n = 0; int pend_slot[13] = {0};  // the exchange in flight: how it was pushed, which planes
   unsigned char *peerL = nullptr, *peerR = nullptr;
   bool peerL_ipc = false, peerR_ipc = false;  // opened with cudaIpcOpenMemHandle (to be closed)
   size_t pbL = 0, pbR = 0;
@@ -439,6 +492,7 @@ int push_ghosts(wsb_sim* s, const XPlanes& xp) {
   const HaloPlanes& hp = xp.hp;
   ProfScope prof(s, WSB_KERNEL_HALO, cs);
   PushArgs a{};
+  a.compact = s->peer_compact ? 1 : 0;
   a.mine = s->arena; a.left = s->peerL; a.right = s->peerR;
   a.pbMine = s->plane_bytes; a.pbLeft = s->pbL; a.pbRight = s->pbR;
   a.pitchMine = s->pitch; a.pitchLeft = s->pitchL; a.pitchRight = s->pitchR;
@@ -455,6 +509,8 @@ int push_ghosts(wsb_sim* s, const XPlanes& xp) {
   LAUNCHED("k_push_ghosts");
   CK(cudaEventRecord(s->evPush, cs));
   s->pending_seq = a.seq;
+  s->pend_compact = s->peer_compact; s->pend_n = hp.n;
+  for (int k = 0; k < hp.n; k++) s->pend_slot[k] = xp.slot[k];
   s->push_pending = true;
   s->exch_pending = true;
   return 0;
@@ -502,6 +558,16 @@ int wait_ghosts(wsb_sim* s, cudaStream_t st) {
   ProfScope prof(s, WSB_KERNEL_WAIT, st);
   k_wait_ghosts<<<1, 1, 0, st>>>(reinterpret_cast<unsigned*>(s->arena + s->plane_bytes * kArenaSlots), s->pending_seq, s->spin_ns);
   LAUNCHED("k_wait_ghosts");
+  if (s->pend_compact) {  // the neighbours' columns are in this rank's landing zones: copy them into the ghost columns
+    UnpackArgs u{};
+    u.mine = s->arena; u.pb = s->plane_bytes; u.pitch = s->pitch; u.lw = s->lw; u.H = s->H;
+    u.vec = (s->pitch % 4 == 0 && s->lw % 4 == 0) ? 1 : 0;
+    u.n = s->pend_n;
+    for (int k = 0; k < u.n; k++) u.slot[k] = s->pend_slot[k];
+    const int threads = 256, blocks = std::min(32, (u.n * s->H * 2 + threads - 1) / threads);
+    k_unpack_zone<<<blocks, threads, 0, st>>>(u);
+    LAUNCHED("k_unpack_zone");
+  }
   return 0;
 }
 // the compute stream may touch the ghost columns again: the neighbours' data of the exchange in flight has arrived
@@ -843,7 +909,7 @@ int alloc_all(wsb_sim* s) {
   const bool strips = s->cfg.n_ranks > 1;
   if (strips) {  // everything a ghost exchange can carry lives in one arena the neighbours map (cudaIpc), flags behind it
     s->plane_bytes = (n * 4 + 255) / 256 * 256;
-    s->arena_bytes = s->plane_bytes * kArenaSlots + (size_t)kNumFlags * kFlagStride * 4;
+    s->arena_bytes = s->plane_bytes * kArenaSlots + kZoneOffset + zone_bytes(s->H);  // planes | flag lines | landing zones
     CK(cudaMalloc(&s->arena, s->arena_bytes));
     CK(cudaMemset(s->arena, 0, s->arena_bytes));
   }
@@ -1097,7 +1163,7 @@ int wsb_create(const wsb_config* cfg, wsb_sim** out) {
        // synchronise the context — behind a neighbour's spinning k_push_ghosts / k_wait_ghosts that would stall
        // (several strips in one process: deadlock until the bounded wait runs out).
       cudaFuncAttributes fa;
-      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_wall_tilemap, (const void*)k_push_ghosts, (const void*)k_ghosts_free,
+      const void* fns[] = {(const void*)k_fused_pvb, (const void*)k_fused_adv, (const void*)k_fused_dry, (const void*)k_wall_tilemap, (const void*)k_push_ghosts, (const void*)k_ghosts_free, (const void*)k_unpack_zone,
                            (const void*)k_wait_ghosts, (const void*)k_pack_halo, (const void*)k_unpack_halo, (const void*)k_precipitation, (const void*)k_boxsum, (const void*)k_clear_origins,
                            (const void*)k_latch, (const void*)k_texels_to_planes, (const void*)k_planes_to_texels, (const void*)k_pressure_rect,
                            (const void*)k_gather_points};
@@ -1307,9 +1373,10 @@ int wsb_set_exchange(wsb_sim* s, int32_t transport) {
   if (s->cfg.n_ranks <= 1) return fail("wsb_set_exchange: not a strip of a multi-GPU run");
   if (use_device(s) || join_exchange(s) || join_push(s)) return 1;
   CK(cudaStreamSynchronize(s->stream));
-  if (transport == WSB_EXCHANGE_PEER) {
+  if (transport == WSB_EXCHANGE_PEER || transport == WSB_EXCHANGE_PEER_COMPACT) {
     if (!s->peerL || !s->peerR) return fail("wsb_set_exchange: the peer transport needs wsb_connect_peers first");
     s->peer_mode = true;
+    s->peer_compact = transport == WSB_EXCHANGE_PEER_COMPACT;
   } else if (transport == WSB_EXCHANGE_NCCL) {
     if (!s->comm) return fail("wsb_set_exchange: the NCCL transport needs a comm_id at wsb_create");
     s->peer_mode = false;

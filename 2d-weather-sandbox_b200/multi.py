@@ -13,6 +13,7 @@ import numpy as np
 from . import strips
 
 COMM_ID_BYTES = 128
+PEERC_MIN_STRIP = 4096  # strip width from which "auto" also times the landing-zone push (profiles/r3_multi_gpu.md)
 
 
 def broadcast_comm_id(create_fn, group=None) -> bytes:
@@ -43,16 +44,20 @@ def calibrate_exchange(sim, iters: int = 12, group=None) -> dict:
     """Time `iters` iterations of the LIVE state with each ghost-exchange transport of a strip that has both
     (transport "auto"), max over ranks, and keep the faster one.  Which one wins depends on the strip width — measured
     on one NVSwitch box: the peer push at 2 and 8 GPUs, NCCL send/recv at 4 (profiles/r3_multi_gpu.md) — and both
-    give bit-identical fields, so this is a pure scheduling decision.  Advances the simulation by 4 * iters
-    iterations; every rank must call it at the same point.  Returns the timings (ms per iteration)."""
+    give bit-identical fields, so this is a pure scheduling decision.  Rings with two distinct neighbours and strips
+    of 4096 columns or more — where the direct push is slow because its stores are scattered over every page of two
+    peer arenas — also try "peerc", the push through a compact landing zone.  Advances the simulation by
+    2 * iters iterations per candidate; every rank must call it at the same point.  Returns the timings (ms per
+    iteration)."""
     import torch
     import torch.distributed as dist
 
-    if getattr(sim, "transports", None) != ("peer", "nccl"):
+    names = tuple(getattr(sim, "transports", None) or ())
+    if len(names) < 2:
         return {}
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     out = {}
-    for name in ("nccl", "peer"):
+    for name in reversed(names):
         sim.set_exchange(name)
         sim.step(iters)  # settle into the transport's steady state
         sim.sync()
@@ -71,8 +76,8 @@ def calibrate_exchange(sim, iters: int = 12, group=None) -> dict:
 def create_distributed(width: int, height: int, *, device: int, gui_controls=None, group=None, transport: str | None = None, **kw):
     """A Simulation for this rank's strip of a width x height grid (torch.distributed must be
     initialised; with world size 1 this is a plain single-GPU simulation).  transport: "peer"
-    (default; WSB_EXCHANGE overrides), "nccl", or "auto" = both set up, peer selected until
-    calibrate_exchange(sim) has timed them on the live state."""
+    (default; WSB_EXCHANGE overrides), "peerc" (peer through a compact landing zone), "nccl", or "auto" = all set
+    up, peer selected until calibrate_exchange(sim) has timed them on the live state."""
     import os
 
     import torch.distributed as dist
@@ -84,7 +89,7 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
     if n == 1:
         return Simulation(width, height, kw.pop("n_droplets", 0), device=device, gui_controls=gui_controls, **kw)
     transport = transport or os.environ.get("WSB_EXCHANGE", "peer")
-    if transport not in ("peer", "nccl", "auto"):
+    if transport not in ("peer", "peerc", "nccl", "auto"):
         raise ValueError(f"unknown ghost-exchange transport {transport!r}")
     kw.pop("n_droplets", None)
     if transport == "nccl":
@@ -105,7 +110,14 @@ def create_distributed(width: int, height: int, *, device: int, gui_controls=Non
     dist.all_gather_object(errs, err, group=group)
     if all(e is None for e in errs):
         sim.transport = "peer"
-        sim.transports = ("peer", "nccl") if transport == "auto" else ("peer",)
+        if transport == "peerc":
+            sim.set_exchange("peerc")
+            sim.transports = ("peerc",)
+        elif transport == "auto":
+            wide_ring = n >= 3 and width // n >= PEERC_MIN_STRIP  # rank-independent: every rank must time the same candidates
+            sim.transports = ("peer", "nccl", "peerc") if wide_ring else ("peer", "nccl")
+        else:
+            sim.transports = ("peer",)
         return sim
     if sim is not None:
         sim.close()

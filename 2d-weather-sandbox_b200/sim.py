@@ -218,8 +218,9 @@ class Simulation:
         self._check(self.L.wsb_connect_peers(self.h, left_info, right_info))
 
     def set_exchange(self, transport: str):
-        """Select the ghost-exchange transport ("peer" or "nccl") of a strip that has both."""
-        self._check(self.L.wsb_set_exchange(self.h, {"nccl": 0, "peer": 1}[transport]))
+        """Select the ghost-exchange transport of a strip: "peer" (stores straight into the neighbours' ghost columns),
+        "peerc" (the same through a compact landing zone + a local copy) or "nccl"."""
+        self._check(self.L.wsb_set_exchange(self.h, {"nccl": 0, "peer": 1, "peerc": 2}[transport]))
         self.transport = transport
 
     # -- state ---------------------------------------------------------------------------------

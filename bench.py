@@ -431,7 +431,8 @@ def run_ours(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms / K, "sustained": sustained, "per_rank": roofline.get("per_rank"),
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms / K, "sustained": sustained, "transport": transport,
+                              "transport_calibration_ms_per_step": calibration, "per_rank": roofline.get("per_rank"),
                               "kernels_ms_per_step": roofline["kernels_ms_per_step"]}), flush=True)
         sim.close()
         if world > 1:

@@ -155,7 +155,11 @@ int wsb_connect_peers(wsb_sim* sim, const uint8_t* left_info, const uint8_t* rig
  * bit-identical either way).  Which one is faster depends on the strip width — measured on one NVSwitch box: peer at
  * 2 and 8 GPUs, NCCL at 4 (profiles/r3_multi_gpu.md) — so the Python host times both on the live state
  * (multi.calibrate_exchange).  Synchronises. */
-enum { WSB_EXCHANGE_NCCL = 0, WSB_EXCHANGE_PEER = 1 };
+/* WSB_EXCHANGE_PEER_COMPACT: the peer transport with a compact landing zone — the neighbours store the 8 ghost columns
+ * of every plane and row into one contiguous 1.7-MB block per side of this rank's arena and the rank copies them into its
+ * ghost columns itself; for rings with two distinct neighbours and wide strips, where stores scattered over every page of
+ * two peer arenas are slow (profiles/r3_multi_gpu.md). */
+enum { WSB_EXCHANGE_NCCL = 0, WSB_EXCHANGE_PEER = 1, WSB_EXCHANGE_PEER_COMPACT = 2 };
 int wsb_set_exchange(wsb_sim* sim, int32_t transport);
 
 /* app.js:5149-5317 + 4885-5002: allocate state; light, feedback, deposition, lightning, curl and

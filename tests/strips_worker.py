@@ -51,6 +51,8 @@ def make_ring(n, W, H, g):
     infos = [s.peer_info() for s in sims]
     for r, s in enumerate(sims):
         s.connect_peers(infos[(r - 1) % n], infos[(r + 1) % n])
+        if os.environ.get("WSB_TEST_EXCHANGE"):  # "peerc": the landing-zone variant of the peer transport
+            s.set_exchange(os.environ["WSB_TEST_EXCHANGE"])
     return sims
 
 
@@ -108,7 +110,7 @@ def _ipc_rank(rank, n, port, W, H, iters, ret):
     dist.init_process_group("gloo", rank=rank, world_size=n)
     try:
         g, base, water, wall = state(W, H)
-        sim = wsb200.multi.create_distributed(W, H, device=0, gui_controls=g, transport="peer")  # every rank on GPU 0
+        sim = wsb200.multi.create_distributed(W, H, device=0, gui_controls=g, transport=os.environ.get("WSB_TEST_EXCHANGE", "peer"))  # every rank on GPU 0
         sim.upload(base, water, wall, None)
         sim.set_frame_inputs(wsb200.params.frame_inputs(g))
         sim.step(iters)

@@ -53,7 +53,7 @@ def _worker(rank, world, port, W, H, iters, ret, transport):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl", "auto"])
+@pytest.mark.parametrize("transport", ["peer", "peerc", "nccl", "auto"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_strips_bit_identical_to_single_gpu(world, transport, tmp_path):
     import torch

@@ -32,6 +32,18 @@ def test_strips_in_one_process_bit_identical_to_single_gpu(n, w, h, iters):
     _run("inproc", n, w, h, iters)
 
 
+@pytest.mark.parametrize("n,w,h,iters", [(2, 512, 96, 20), (3, 600, 80, 14), (4, 1024, 64, 12), (4, 320, 64, 10)])
+def test_landing_zone_push_in_one_process_bit_identical_to_single_gpu(n, w, h, iters):
+    """Transport "peerc": the neighbours store into this rank's compact landing zones, k_unpack_zone copies them into
+    the ghost columns — with one neighbour on both sides (n = 2), with two distinct neighbours (n = 3, 4), with interior
+    tile columns (two-stream schedule) and without (320 / 4 = 80 columns)."""
+    _run("inproc", n, w, h, iters, env={"WSB_TEST_EXCHANGE": "peerc"})
+
+
+def test_landing_zone_push_in_two_processes_over_cuda_ipc():
+    _run("ipc", 2, 512, 96, 12, env={"WSB_TEST_EXCHANGE": "peerc"})
+
+
 def test_dry_strips_in_one_process_bit_identical_to_single_gpu():
     _run("inproc", 2, 512, 96, 10, "dry")
 
