@@ -502,8 +502,9 @@ def run_ours(args):
 
     partition = "single GPU"
     if world > 1:
-        how = ("k_push_ghosts: edge columns stored straight into the neighbours' ghost columns over NVLink (cudaIpc windows), sequence flags"
-               if transport == "peer" else "pack + ncclSend/ncclRecv + unpack")
+        how = {"peer": "k_push_ghosts: edge columns stored straight into the neighbours' ghost columns over NVLink (cudaIpc windows), sequence flags",
+               "peerc": "k_push_ghosts: edge columns stored into the neighbours' compact landing zones over NVLink (cudaIpc windows), sequence flags, "
+                        "k_unpack_zone copies them into the ghost columns"}.get(transport, "pack + ncclSend/ncclRecv + unpack")
         partition = f"{world} x-strip(s) of {lw} columns, ghost {gh}, one ring exchange per iteration ({how})"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
