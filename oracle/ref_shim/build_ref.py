@@ -23,32 +23,28 @@ FLAGS = ["-O3", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fas
 
 
 def build(ref_root: str = "/root/reference", force: bool = False, extra_flags=(), out: str | None = None) -> str | None:
-    """extra_flags / out: experiment builds (e.g. -DWSB_REF_LIBM, -ffp-contract=fast) beside the canonical library."""
-    global LIB
-    if out is not None:
-        saved, LIB = LIB, out
-        try:
-            return build(ref_root, True, extra_flags)
-        finally:
-            LIB = saved
+    """Build (when stale) and return the library path; None when there is neither a checkout nor a prebuilt library.
+    extra_flags / out: experiment builds beside the canonical library (e.g. -DWSB_REF_LIBM, -ffp-contract=fast;
+    profiles/tools/freeze_sensitivity.py)."""
+    lib = out or LIB
     shaders = os.path.join(ref_root, "shaders")
     if not os.path.isdir(shaders):
-        return LIB if os.path.exists(LIB) else None
+        return lib if os.path.exists(lib) else None
     srcs = [os.path.join(HERE, f) for f in ("translate.py", "glsl_shim.h", "ref_driver.cpp")]
     srcs += [os.path.join(dp, f) for dp, _, fs in os.walk(shaders) for f in fs]
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in srcs):
-        return LIB
-    os.makedirs(OUT, exist_ok=True)
+    if not (force or out) and os.path.exists(lib) and os.path.getmtime(lib) >= max(os.path.getmtime(p) for p in srcs):
+        return lib
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
     gen = tempfile.mkdtemp(prefix="wsb_ref_gen_")  # the translated shader text is an intermediate: only the .so is kept
     try:
         subprocess.check_call([sys.executable, os.path.join(HERE, "translate.py"), shaders, gen], stdout=subprocess.DEVNULL)
-        subprocess.check_call([CXX] + FLAGS + list(extra_flags) + ["-I", HERE, "-I", gen, "-o", LIB, os.path.join(HERE, "ref_driver.cpp")])
+        subprocess.check_call([CXX] + FLAGS + list(extra_flags) + ["-I", HERE, "-I", gen, "-o", lib, os.path.join(HERE, "ref_driver.cpp")])
     finally:
         if os.environ.get("WSB_KEEP_REF_GEN"):
             print("generated headers kept in", gen)
         else:
             shutil.rmtree(gen, ignore_errors=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
