@@ -411,6 +411,33 @@ def test_sun_fetch_bit_identical_at_every_sun_angle_on_power_of_two_grids(w, h):
         assert not bad, f"{w}x{h}, sun at {gui_angle} degrees: {bad}"
 
 
+def test_dry_sweep_equals_the_reference_passes_it_is_made_of():
+    """BASELINE config 2 (the >= 70 % roofline kernel k_fused_dry) is velocity -> advection -> pressure of the BASE field
+    with the boundary pass left out — a schedule the bench defines, made of reference passes.  oracle.step_dry (the
+    GPU dry sweep's bar) against the reference's velocityShader / advectionShader / pressureShader run in that order."""
+    w, h, iters = 256, 64, 12
+    base, water, wall = wsb200.synth.dry_state(w, h, seed=1234)
+    base[..., :2] *= f32(3.0)
+    wall[24:34, 100:120, 1] = 0
+    wall[24:34, 100:120, 0] = 1
+    g = P.resolve_settings(None)
+    g["dragMultiplier"], g["wind"] = 0.001, 0.0
+    g["enablePrecipitation"] = False
+    ora = make_oracle(g, base, water, wall, None)
+    ref = make_ref(g, base, water, wall, None)
+    for _ in range(iters):
+        ref.run_pass(0)  # velocityShader: frameBuff_0 -> frameBuff_1
+        ref.field(O.FIELD_BASE, 0, copy=False)[...] = ref.field(O.FIELD_BASE, 1, copy=False)  # no boundary pass in between
+        ref.field(O.FIELD_WALL, 0, copy=False)[...] = ref.field(O.FIELD_WALL, 1, copy=False)
+        ref.run_pass(4)  # advectionShader: frameBuff_0 -> frameBuff_1
+        ref.run_pass(5)  # pressureShader:  frameBuff_1 -> frameBuff_0
+        ref.run_pass(8)  # iterNum++
+    ora.step_dry(iters)
+    got, want = ora.field(O.FIELD_BASE, 0), ref.field(O.FIELD_BASE, 0)
+    assert np.array_equal(got, want), f"dry sweep: base differs in {(got != want).sum()} values"
+    assert np.abs(want[..., :2]).max() > 0.05
+
+
 @pytest.mark.parametrize("w,h,seed,mult", [(256, 128, 0.37, 0.5), (300, 100, 0.81, 0.9), (128, 64, 0.5, 0.07), (64, 64, 0.1, 0.01), (1000, 250, 0.2566, 0.33), (2000, 300, 0.37, 1.0)])
 def test_setup_shader_matches_synth_setup_state(w, h, seed, mult):
     """setupShader.frag (the reference's own, compiled) drawn once == synth.setup_state, bit for bit."""
