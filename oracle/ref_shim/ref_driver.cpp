@@ -7,7 +7,8 @@
 // and never enter the repository.  This file is the part of the reference that is JavaScript and therefore has
 // to be restated: the GL objects of app.js:5118-5317 (textures and their sampling state), the sampler -> texture
 // unit assignments of app.js:5486-5640, the draw loop of app.js:5830-6005 (which texture is bound to which unit
-// and which framebuffer receives which outputs), transform feedback + additive point sprites of the particle
+// and which framebuffer receives which outputs; attachments: frameBuff_N = base_N / water_N / wall_N app.js:5244-5252,
+// lightFrameBuff_N 5282-5294, feedback + deposition 5308-5309, lightning 5317), transform feedback + additive point sprites of the particle
 // pass, and the fixed-function steps GL performs around a shader (varying interpolation at pixel centres,
 // RGBA8I saturation, point rasterisation, blending) in the canonical forms of DESIGN.md "Spec freeze".
 //
