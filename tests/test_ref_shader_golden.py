@@ -118,7 +118,7 @@ def test_cuda_reproduces_the_reference_shader_vectors(name, schedule, gold):
     sim.close()
 
 
-@pytest.mark.parametrize("name,snaps", [("stress", (1, 10)), ("save100_dry", (1, 10))])
+@pytest.mark.parametrize("name,snaps", [("stress", (1, 10)), ("save100_dry", (1, 10)), ("hotlake", (100,))])
 def test_fused_kernels_on_the_emulator_reproduce_the_reference_shader_vectors(name, snaps, gold, emu):
     """csrc/wsb_fused_kernels.cuh compiled unchanged for the host emulation of the CUDA execution model
     (tests/host_cells/): the product's kernels against the reference's shaders without a GPU, bit for bit."""
